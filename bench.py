@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- image pairs/s of the unsupervised flow+occlusion training step (BASELINE.json config 2/3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One step = general_step_occ_aware (2 network forwards, range-map occlusion, fused occlusion-weighted loss,
+smoothness) + weighted loss + backward + gradient all-reduce (N>1) + Adam, on a synthetic FlyingChairs-shaped
+batch (8 pairs of 384x512 per GPU).  Prints ONE JSON line (rank 0).
+
+  value     pairs/s, batch resident in HBM, CUDA-event timed, max over ranks
+  e2e       same step through the public API with the batch in pinned HOST memory: H2D of the batch and a D2H read of
+            the loss inside the timed region, every step
+  roofline  the dominant hot-path kernel of the step, timed alone on the step's own shapes with an L2 flush between
+            launches: algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle port of the same step on the host cores (bounded sample), rank 0, N=1 only
+
+--impl reference times the reference's CPU algorithm (the oracle port: the reference is Python and cannot travel to
+the GPU box) on the host cores and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "image pairs/sec (fwd+bwd flow+occ step, 384x512)"
+UNIT = "pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--batch", type=int, default=8, help="image pairs per GPU")
+    ap.add_argument("--height", type=int, default=384)
+    ap.add_argument("--width", type=int, default=512)
+    ap.add_argument("--graph", type=int, default=1, help="capture the whole step in a CUDA graph (1) or run eagerly (0)")
+    ap.add_argument("--tf32", type=int, default=0, help="allow TF32 cuDNN convolutions (torch's default); 0 = strict fp32")
+    ap.add_argument("--cpu-sample-batch", type=int, default=2)
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-roofline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.stop = threading.Event()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the same step on the host cores
+# ------------------------------------------------------------------------------------------------------------
+def cpu_step_runner(batch_size, height, width):
+    """Returns (run_one_step, cores): one occ-aware step fwd+bwd+Adam of the oracle port on the CPU."""
+    import torch
+    from oracle import ocflow_oracle as O
+    from ocflow_b200.flow_net_cv import FlowNetCV   # only for parameter shapes / the reference's default init
+    from ocflow_b200.train import DEFAULT_HPARAMS
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    net = FlowNetCV(DEFAULT_HPARAMS["displacement"])
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    opt = torch.optim.Adam(list(sd.values()), DEFAULT_HPARAMS["learning_rate"])
+    g = torch.Generator().manual_seed(1234)
+    imgs = torch.rand(batch_size, 6, height, width, generator=g) * 2 - 1
+    flow = torch.randn(batch_size, 2, height, width, generator=g) * 5
+    occ = (torch.rand(batch_size, 1, height, width, generator=g) < 0.3).float()
+
+    def run():
+        opt.zero_grad(set_to_none=True)
+        losses = O.occ_aware_step(sd, (imgs, flow, occ), DEFAULT_HPARAMS["displacement"])
+        loss = O.total_loss(losses, DEFAULT_HPARAMS["photo_weight"], DEFAULT_HPARAMS["smooth1_weight"], DEFAULT_HPARAMS["smooth2_weight"])
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    return run, torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # other ranks exit 0 without work
+    b = args.cpu_sample_batch if (args.steps + args.warmup) <= 30 else 1
+    run, cores = cpu_step_runner(b, args.height, args.width)
+    for _ in range(min(args.warmup, 2)):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run()
+    dt = time.perf_counter() - t0
+    value = b * args.steps / dt
+    sample = "%d steps x %d of %d pairs at %dx%d (oracle port of models/model.py:366-436, torch CPU fp32, %d threads)" % (
+        args.steps, b, args.batch, args.height, args.width, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "unsupervised flow+occlusion training step, FlyingChairs shape %dx%d, batch %d per GPU" % (
+            args.height, args.width, args.batch), "cpu_sample_batch": b},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# roofline leg: every hot-path kernel alone on the step's shapes
+# ------------------------------------------------------------------------------------------------------------
+def kernel_table(args, torch):
+    """name -> (callable launching exactly that kernel, algorithmic bytes, launches per training step)."""
+    from ocflow_b200 import _lib, ops
+    import ctypes
+
+    B, H, W = args.batch, args.height, args.width
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(1)
+    table = {}
+    levels = {6: 196, 5: 128, 4: 96, 3: 64, 2: 32}
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def P(t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    for lvl, C in levels.items():
+        h, w = H >> lvl, W >> lvl
+        n = B * h * w
+        f1 = torch.randn(B, C, h, w, device=dev, generator=g)
+        f2 = torch.randn(B, C, h, w, device=dev, generator=g)
+        fl = torch.randn(B, 2, h, w, device=dev, generator=g) * 2
+        out = torch.empty(B, 81, h, w, device=dev)
+        gout = torch.randn(B, 81, h, w, device=dev, generator=g)
+        d1, d2 = torch.empty_like(f1), torch.empty_like(f2)
+        wout = torch.empty_like(f2)
+        dfl = torch.empty_like(fl)
+        table["corr_fwd_L%d" % lvl] = (lambda f1=f1, f2=f2, out=out, C=C, h=h, w=w: _lib.call(
+            "ocf_corr_fwd", P(f1), P(f2), P(out), B, C, h, w, 4, 0, 0.1, None, st), 4 * n * (2 * C + 81), 2)
+        table["corr_bwd_L%d" % lvl] = (lambda gout=gout, out=out, f1=f1, f2=f2, d1=d1, d2=d2, C=C, h=h, w=w: _lib.call(
+            "ocf_corr_bwd", P(gout), P(out), P(f1), P(f2), P(d1), P(d2), B, C, h, w, 4, 0, 0.1, st), 4 * n * (81 + 4 * C), 1)
+        if lvl < 6:
+            table["warp_fwd_L%d" % lvl] = (lambda f2=f2, fl=fl, wout=wout, C=C, h=h, w=w: _lib.call(
+                "ocf_warp_fwd", P(f2), P(fl), None, P(wout), B, C, h, w, 0, 1.25, st), 4 * n * (2 * C + 2), 2)
+            table["warp_bwd_L%d" % lvl] = (lambda f2=f2, fl=fl, wout=wout, d2=d2, dfl=dfl, C=C, h=h, w=w: _lib.call(
+                "ocf_warp_bwd", P(wout), P(f2), P(fl), None, P(d2), P(dfl), None, B, C, h, w, 0, 1.25, st), 4 * n * (3 * C + 4), 1)
+    # loss level
+    n = B * H * W
+    i1 = torch.rand(B, 3, H, W, device=dev, generator=g) * 2 - 1
+    i2 = torch.rand(B, 3, H, W, device=dev, generator=g) * 2 - 1
+    fw = torch.randn(B, 2, H, W, device=dev, generator=g) * 5
+    fg = torch.randn(B, 2, H, W, device=dev, generator=g) * 5
+    og = (torch.rand(B, 1, H, W, device=dev, generator=g) < 0.3).float()
+    rm = torch.empty(B, 1, H, W, device=dev)
+    sums = torch.zeros(8, device=dev, dtype=torch.float64)
+    dflow = torch.empty_like(fw)
+    table["range_map"] = (lambda: _lib.call("ocf_range_map", P(fw), P(rm), None, B, H, W, st), 4 * n * 4, 1)
+    table["occ_photo_fused"] = (lambda: _lib.call("ocf_occ_photo_fused", P(i1), P(i2), P(fw), P(rm), P(fg), P(og), P(sums), P(dflow), None,
+                                                  B, 3, H, W, 0.001, st), 4 * n * 14, 1)
+    return table
+
+
+def time_kernels(args, torch):
+    table = kernel_table(args, torch)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")  # 256 MB > 126 MB L2
+    res = {}
+    for name, (fn, nbytes, per_step) in table.items():
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        times = []
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1) * 1e-3)
+        t = statistics.mean(times)
+        res[name] = {"us": t * 1e6, "gbs": nbytes / t / 1e9, "bytes": nbytes, "per_step": per_step}
+    return res
+
+
+# ------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from ocflow_b200 import _lib
+    from ocflow_b200.train import TrainStep, build_model, synthetic_batch
+
+    _lib.load()
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = bool(args.tf32)
+    torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
+    B, H, W = args.batch, args.height, args.width
+    model = build_model(seed=0)
+    step = TrainStep(model, use_graph=bool(args.graph))
+    batch = synthetic_batch(B, H, W, "cuda", 1234 + rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 3)):
+        step.step(batch)
+    barrier()
+    l0 = _lib.launch_count
+    # launches per step: one eager step of the same model outside the timed region (graph replays do not go through ctypes)
+    if args.graph:
+        step._eager(batch)
+        per_step_launches = _lib.launch_count - l0
+    barrier()
+
+    # ---- timed region: HBM-resident batch ----
+    with ClockSampler(local) as clk:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l1 = _lib.launch_count
+        e0.record()
+        for _ in range(args.steps):
+            loss = step.step(batch)
+        e1.record()
+        barrier()
+        dt = e0.elapsed_time(e1) * 1e-3
+        if not args.graph:
+            per_step_launches = (_lib.launch_count - l1) // max(args.steps, 1)
+    tmax = torch.tensor([dt], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dt = float(tmax)
+    final_loss = float(loss)
+
+    # ---- e2e: pinned host batch -> H2D every step, loss read back every step ----
+    host = tuple(t.cpu().pin_memory() for t in batch)
+    dev = tuple(torch.empty_like(t) for t in batch)
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    for _ in range(2):
+        for d, h in zip(dev, host):
+            d.copy_(h, non_blocking=True)
+        float(step.step(dev))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        for d, h in zip(dev, host):
+            d.copy_(h, non_blocking=True)
+        lv = float(step.step(dev))   # D2H read of the step's result (4 bytes) + host sync, every step
+    e1.record()
+    barrier()
+    dte = torch.tensor([e0.elapsed_time(e1) * 1e-3], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dte, op=dist.ReduceOp.MAX)
+    dte = float(dte)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    line = {
+        "metric": METRIC, "value": world * B * args.steps / dt, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "unsupervised flow+occlusion training step (FlowNetCV 'pwc', occ_aware), FlyingChairs shape %dx%d, "
+                               "batch %d per GPU, Adam" % (H, W, B),
+                   "global_batch": world * B, "parallelism": "dp%d" % world, "cuda_graph": bool(args.graph),
+                   "conv_math": "tf32 (torch default)" if args.tf32 else "strict fp32 (cudnn.allow_tf32=False)",
+                   "l2_policy": "working set per step (>1 GB of activations) exceeds the 126 MB L2; kernel-alone timings flush L2 "
+                                "with a 256 MB memset between launches"},
+        "e2e": {"value": world * B * args.steps / dte, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": int(per_step_launches * args.steps),
+        "clocks": clk.summary(), "final_loss": final_loss,
+    }
+
+    # ---- roofline of the dominant hot-path kernel ----
+    if not args.skip_roofline:
+        peak, peak_src = measured_peaks()
+        kt = time_kernels(args, torch)
+        dom = max(kt, key=lambda k: kt[k]["us"] * kt[k]["per_step"])
+        line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": kt[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                            "frac": kt[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                            "launch_us": kt[dom]["us"], "algorithmic_bytes": kt[dom]["bytes"]}
+        line["kernels"] = {k: {"us": round(v["us"], 2), "gbs": round(v["gbs"], 1), "frac": round(v["gbs"] / peak, 3),
+                               "per_step": v["per_step"]} for k, v in kt.items()}
+        line["hot_path_us_per_step"] = round(sum(v["us"] * v["per_step"] for v in kt.values()), 1)
+
+    # ---- CPU baseline (oracle port), bounded sample ----
+    if world == 1 and not args.skip_cpu:
+        b = args.cpu_sample_batch
+        run, cores = cpu_step_runner(b, H, W)
+        run()
+        t0 = time.perf_counter()
+        nrep = 2
+        for _ in range(nrep):
+            run()
+        cdt = (time.perf_counter() - t0) / nrep
+        line["cpu_baseline"] = {"value": b / cdt, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "%d steps x %d of %d pairs at %dx%d after 1 warm-up (oracle port, torch CPU fp32)" % (nrep, b, B, H, W)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

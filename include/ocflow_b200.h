@@ -1,0 +1,193 @@
+/*
+ * ocflow_b200 -- C ABI of the B200 (sm_100a) hot path of OCFlow.
+ *
+ * The reference (dongliangcao/OCFlow) is pure Python/PyTorch and has no FFI layer; its "plugin
+ * boundary" for this path is a set of Python symbols.  This header declares the
+ * C entry points that the Python mirror of those symbols (package ocflow_b200) binds with ctypes --
+ * i.e. exactly what a maintainer of the reference would bind to replace each symbol.  Every entry
+ * cites the reference interface it replaces (file:line relative to the reference root).
+ *
+ * Conventions (all entry points):
+ *   - tensors are fp32, NCHW, contiguous unless a stride argument says otherwise; pointers are DEVICE
+ *     pointers except in the ocf_host_* entry points, which take HOST pointers;
+ *   - the caller owns every buffer (inputs, outputs, workspaces); nothing is allocated, freed or
+ *     cached inside the library and there is no global mutable state => re-entrant;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*) and the call returns without
+ *     synchronising => CUDA-graph capturable; scatter targets are zeroed inside the call;
+ *   - return value: 0 = OCF_OK, negative = OCF_E* argument error (nothing was launched),
+ *     positive = cudaError_t reported by the launch;
+ *   - there is NO CPU fallback and no dispatch on device type.
+ */
+#ifndef OCFLOW_B200_H
+#define OCFLOW_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* ocf_stream_t; /* cudaStream_t */
+
+#define OCF_OK 0
+#define OCF_ENULL (-1)        /* required pointer is NULL */
+#define OCF_ESHAPE (-2)       /* non-positive or inconsistent dimension */
+#define OCF_EUNSUPPORTED (-3) /* argument value outside what the kernels implement */
+#define OCF_EALIGN (-4)       /* pointer not aligned to 4 bytes / stride not usable */
+
+#define OCF_ABI_VERSION 1
+#define OCF_MAX_DISPLACEMENT 16
+
+int ocf_abi_version(void);
+/* 100 for sm_100a builds */
+int ocf_build_sm(void);
+/* static string for an OCF_E* code or a cudaError_t */
+const char* ocf_error_string(int code);
+
+/* ---------------------------------------------------------------------------------------------
+ * Cost volume.   Replaces compute_cost_volume(features1, features2, max_displacement=4)
+ *                models/networks/correlation_layer.py:7-40 and the missing CostVolumeLayer
+ *                (call sites cost_volume_flow_occ_net.py:53,188; flow_occ_net_c.py:26,99).
+ *   out[b, (dy+d)*(2d+1)+(dx+d), y, x] = act( (1/C) * sum_c f1[b,c,y,x] * f2[b,c,y+dy,x+dx] )
+ *   zero outside the image.  act = LeakyReLU(leaky_slope) when leaky_slope != 1 (the callers'
+ *   next op, cost_volume_flow_net.py:173); pass 1.0f for the bare cost volume.
+ *   out_bstride: elements between consecutive batch items of `out` (>= (2d+1)^2*H*W) so the result
+ *   can be written straight into a wider channel-concatenated buffer; 0 means dense.
+ *   norm: optional DEVICE pointer to {mean, inv_std}; when non-NULL both inputs are normalised on the
+ *   fly as (x-mean)*inv_std inside the image (normalize_features with default flags,
+ *   correlation_layer.py:42-82, fused with the correlation).
+ * ------------------------------------------------------------------------------------------- */
+int ocf_corr_fwd(const float* f1, const float* f2, float* out, int B, int C, int H, int W, int d,
+                 long long out_bstride, float leaky_slope, const float* norm, ocf_stream_t stream);
+
+/* Backward of the above (autograd of correlation_layer.py:33-39).
+ *   df1[b,c,y,x] = (1/C) sum_k g'[b,k,y,x] * f2[b,c,y+dy,x+dx]
+ *   df2[b,c,y,x] = (1/C) sum_k g'[b,k,y-dy,x-dx] * f1[b,c,y-dy,x-dx]
+ *   g' = grad_out, or grad_out * LeakyReLU'(out_act) when out_act != NULL (out_act = the activated
+ *   forward output, same strides as grad_out).  df1 or df2 may be NULL (not needed).
+ *   g_bstride: batch stride of grad_out/out_act in elements, 0 = dense. */
+int ocf_corr_bwd(const float* grad_out, const float* out_act, const float* f1, const float* f2,
+                 float* df1, float* df2, int B, int C, int H, int W, int d, long long g_bstride,
+                 float leaky_slope, ocf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Feature normalisation.  Replaces normalize_features(feature_list, normalize, center,
+ *   moments_across_channels, moments_across_images)  models/networks/correlation_layer.py:42-82.
+ *   All T tensors of the list must share one shape [B,C,H,W] (they do at every call site).
+ *   flags: bit0 normalize, bit1 center, bit2 moments_across_channels, bit3 moments_across_images.
+ *   stats workspace (device, caller-owned): 2*T*B*G floats of per-group {mean, var} followed by
+ *   2*T*B*G floats of the {mean, inv_std} actually applied, G = 1 (across channels) or C.
+ * ------------------------------------------------------------------------------------------- */
+#define OCF_NORM_NORMALIZE 1
+#define OCF_NORM_CENTER 2
+#define OCF_NORM_ACROSS_CHANNELS 4
+#define OCF_NORM_ACROSS_IMAGES 8
+int ocf_normalize_fwd(const float* const* xs, float* const* ys, int T, int B, int C, int H, int W,
+                      int flags, float* stats, ocf_stream_t stream);
+/* grads wrt every input, differentiating through the statistics (no detach in the reference).
+ * red workspace: 2*T*B*G floats. */
+int ocf_normalize_bwd(const float* const* grad_ys, const float* const* xs, float* const* grad_xs,
+                      int T, int B, int C, int H, int W, int flags, const float* stats, float* red,
+                      ocf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Bilinear backward warp.  Replaces the 11 `warp`/`backwarp` bodies:
+ *   align_corners=1: utils.py:20-58 (is_mask), models/model.py:191-221, 962-992, 1159-1189,
+ *                    models/flow_model.py:49-79, models/networks/pwc_net.py:6-29
+ *   align_corners=0: cost_volume_flow_net.py:121-151, cost_volume_flow_occ_net.py:137-167,419-449,
+ *                    flow_net.py:57-87, flow_occ_net.py:96-126, inpainting_model.py:22-52
+ *   out[b,c,y,x] = bilinear(img[b,c], ix, iy), zero padding, 4 taps bounds-tested independently;
+ *   (ix,iy) reproduce the reference's normalise / ATen's un-normalise op order in fp32.
+ *   flags: bit0 align_corners, bit1 is_mask (utils.py:49-57).
+ *   scale: multiplies flow before use (the callers' `up_flow*0.625` etc., cost_volume_flow_net.py:186).
+ *   occ: optional [B,1,H,W] multiplier applied to the output (the "woc" chain,
+ *        cost_volume_flow_occ_net.py:204-205); NULL = none.
+ * ------------------------------------------------------------------------------------------- */
+#define OCF_WARP_ALIGN_CORNERS 1
+#define OCF_WARP_IS_MASK 2
+int ocf_warp_fwd(const float* img, const float* flow, const float* occ, float* out, int B, int C, int H,
+                 int W, int flags, float scale, ocf_stream_t stream);
+/* d_img (scatter, zeroed inside), d_flow (already multiplied by `scale`), d_occ: each may be NULL. */
+int ocf_warp_bwd(const float* grad_out, const float* img, const float* flow, const float* occ,
+                 float* d_img, float* d_flow, float* d_occ, int B, int C, int H, int W, int flags,
+                 float scale, ocf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Range map / occlusion.  Replaces compute_range_map (models/model.py:243-305 =
+ *   models/flow_model.py:101-163) with flow_to_warp (:223-241) folded in, and optionally
+ *   occ = 1 - clamp(range, 0, 1) (models/model.py:391).
+ *   range_out [B,1,H,W] is zeroed inside the call; occ_out may be NULL.
+ * ------------------------------------------------------------------------------------------- */
+int ocf_range_map(const float* flow, float* range_out, float* occ_out, int B, int H, int W,
+                  ocf_stream_t stream);
+/* flow_to_warp: [B,H,W,2] -> [B,H,W,2] endpoints (models/model.py:223-241) */
+int ocf_flow_to_warp(const float* flow_bhw2, float* out_bhw2, int B, int H, int W, ocf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Charbonnier / photometric.  Replaces robust_l1 (models/model.py:27-35), charbonnier_loss
+ *   (utils.py:8-18) and photometric_error(img_pred, img, occ) (models/model.py:37-46).
+ * ------------------------------------------------------------------------------------------- */
+int ocf_robust_l1_fwd(const float* x, float* y, long long n, float alpha, ocf_stream_t stream);
+int ocf_robust_l1_bwd(const float* grad_y, const float* x, float* grad_x, long long n, float alpha,
+                      ocf_stream_t stream);
+/* sums[0] = sum rho(pred-img)*(1-occ) (or sum rho when occ==NULL), sums[1] = sum (1-occ) over B*H*W.
+ * `sums` (2 doubles, device) is zeroed inside.  The scalar loss is assembled by the host mirror:
+ * sums[0]/(3*sums[1]+1e-16) resp. sums[0]/n. */
+int ocf_photometric_fwd(const float* pred, const float* img, const float* occ, double* sums, int B, int C,
+                        int H, int W, float alpha, ocf_stream_t stream);
+/* coef (device, 2 floats): d loss/d sums[0], d loss/d sums[1].  Any of d_pred/d_img/d_occ may be NULL. */
+int ocf_photometric_bwd(const float* pred, const float* img, const float* occ, const float* coef,
+                        float* d_pred, float* d_img, float* d_occ, int B, int C, int H, int W, float alpha,
+                        ocf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Smoothness.  Replaces gradient (models/model.py:53-66), first_order_smoothness_loss (:93-101) and
+ *   second_order_smoothness_loss (:103-114).  order = 1 or 2.  img [B,Ci,H,W], flow [B,Cf,H,W].
+ *   sums (2 doubles, device, zeroed inside): sum_x, sum_y of w*rho(.) ; the host divides by the
+ *   element counts and halves.
+ * ------------------------------------------------------------------------------------------- */
+int ocf_smooth_fwd(const float* img, const float* flow, double* sums, int B, int Ci, int Cf, int H, int W,
+                   int order, float alpha_edge, float alpha_rho, ocf_stream_t stream);
+/* coef (device, 2 floats): d loss / d sums[0..1].  d_img / d_flow are zeroed inside; may be NULL. */
+int ocf_smooth_bwd(const float* img, const float* flow, const float* coef, float* d_img, float* d_flow,
+                   int B, int Ci, int Cf, int H, int W, int order, float alpha_edge, float alpha_rho,
+                   ocf_stream_t stream);
+/* forward differences with a stride (models/model.py:53-66): dx [B,C,H,W-s], dy [B,C,H-s,W] */
+int ocf_gradient(const float* img, float* dx, float* dy, int B, int C, int H, int W, int stride,
+                 ocf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused occlusion-aware loss pass (one kernel per pyramid level of the loss):
+ *   replaces the chain models/model.py:379,391,394,403,405,407 --
+ *   warp(img2, flow) [align_corners=True] -> occ = 1-clamp(range,0,1) -> photometric(occ) ->
+ *   photometric(1-occ) -> mse(flow, flow_gt) -> bce(occ_gt, occ), and emits the un-normalised
+ *   d photo / d flow in the same pass.
+ *   sums (8 doubles, device, zeroed inside):
+ *     [0] sum rho*(1-occ)  [1] sum (1-occ)  [2] sum rho*occ  [3] sum occ
+ *     [4] sum (flow-flow_gt)^2  [5] sum bce(occ_gt, occ)  [6..7] reserved
+ *   dflow_unit [B,2,H,W] (may be NULL): sum_c rho'(diff_c)*(1-occ)*d warp_c/d(u,v).
+ *   range_map / flow_gt / occ_gt may be NULL (terms skipped; occ = 0 when range_map is NULL).
+ * ------------------------------------------------------------------------------------------- */
+int ocf_occ_photo_fused(const float* img1, const float* img2, const float* flow, const float* range_map,
+                        const float* flow_gt, const float* occ_gt, double* sums, float* dflow_unit,
+                        float* warped_out, int B, int C, int H, int W, float alpha, ocf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Supervised losses (a-13): sums of |a-b| / (a-b)^2 / BCE / focal-BCE, one pass.
+ *   kind: 0 = L1, 1 = MSE, 2 = BCE(p, target), 3 = focal(gamma=2) BCE
+ *   (flow_model.py:173-186, flow_occ_model.py:48-55, occlusion_model.py:45-62).
+ *   sum_out: 1 double (device, zeroed inside).  grad (may be NULL): d sum / d a, elementwise.
+ * ------------------------------------------------------------------------------------------- */
+int ocf_pair_loss(const float* a, const float* b, double* sum_out, float* grad, long long n, int kind,
+                  ocf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-buffer convenience entry points (HOST pointers; allocate, copy in, run, copy out, free,
+ * synchronise).  They exist so the C ABI can be exercised end-to-end without any Python/torch.
+ * ------------------------------------------------------------------------------------------- */
+int ocf_host_corr_fwd(const float* f1, const float* f2, float* out, int B, int C, int H, int W, int d);
+int ocf_host_warp_fwd(const float* img, const float* flow, float* out, int B, int C, int H, int W, int flags);
+int ocf_host_range_map(const float* flow, float* range_out, int B, int H, int W);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCFLOW_B200_H */

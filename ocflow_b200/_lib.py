@@ -1,0 +1,92 @@
+"""ctypes binding of libocflow_b200.so (the C ABI declared in include/ocflow_b200.h).
+
+The library is the ONLY compute path of this package: there is no CPU fallback and no other backend.
+If it is missing the import of any op fails loudly (RuntimeError) instead of degrading.
+"""
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libocflow_b200.so")
+
+c_f = ctypes.c_void_p  # device (or host) float* / double* passed as raw addresses
+c_i = ctypes.c_int
+c_ll = ctypes.c_longlong
+c_fl = ctypes.c_float
+c_s = ctypes.c_void_p  # cudaStream_t
+
+# name -> argtypes ; every entry returns int.  Must list every symbol of include/ocflow_b200.h
+# (tests/test_abi.py cross-checks this table against the header).
+SIGNATURES = {
+    "ocf_corr_fwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_ll, c_fl, c_f, c_s],
+    "ocf_corr_bwd": [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_ll, c_fl, c_s],
+    "ocf_normalize_fwd": [c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_s],
+    "ocf_normalize_bwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_s],
+    "ocf_warp_fwd": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_s],
+    "ocf_warp_bwd": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_s],
+    "ocf_range_map": [c_f, c_f, c_f, c_i, c_i, c_i, c_s],
+    "ocf_flow_to_warp": [c_f, c_f, c_i, c_i, c_i, c_s],
+    "ocf_robust_l1_fwd": [c_f, c_f, c_ll, c_fl, c_s],
+    "ocf_robust_l1_bwd": [c_f, c_f, c_f, c_ll, c_fl, c_s],
+    "ocf_photometric_fwd": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_s],
+    "ocf_photometric_bwd": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_s],
+    "ocf_smooth_fwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_fl, c_fl, c_s],
+    "ocf_smooth_bwd": [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_fl, c_fl, c_s],
+    "ocf_gradient": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_s],
+    "ocf_occ_photo_fused": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_s],
+    "ocf_pair_loss": [c_f, c_f, c_f, c_f, c_ll, c_i, c_s],
+    "ocf_host_corr_fwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i],
+    "ocf_host_warp_fwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i],
+    "ocf_host_range_map": [c_f, c_f, c_i, c_i, c_i],
+}
+NOARG = {"ocf_abi_version": c_i, "ocf_build_sm": c_i}
+
+_lib = None
+
+
+def load():
+    """dlopen the library (once) and attach prototypes.  Raises RuntimeError when it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "ocflow_b200: %s is missing -- build it with `python -m ocflow_b200.build` "
+            "(or __graft_entry__.build()); there is no fallback path." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_i
+    for name, res in NOARG.items():
+        fn = getattr(lib, name)
+        fn.argtypes = []
+        fn.restype = res
+    lib.ocf_error_string.argtypes = [c_i]
+    lib.ocf_error_string.restype = ctypes.c_char_p
+    _lib = lib
+    return lib
+
+
+def error_string(code):
+    return load().ocf_error_string(int(code)).decode()
+
+
+# launch counter: every successful C-ABI call that enqueues kernels bumps it (bench.py's gpu_launches)
+launch_count = 0
+KERNELS_PER_CALL = {
+    "ocf_corr_fwd": 1, "ocf_corr_bwd": 1, "ocf_normalize_fwd": 3, "ocf_normalize_bwd": 3, "ocf_warp_fwd": 1,
+    "ocf_warp_bwd": 1, "ocf_range_map": 1, "ocf_flow_to_warp": 1, "ocf_robust_l1_fwd": 1, "ocf_robust_l1_bwd": 1,
+    "ocf_photometric_fwd": 1, "ocf_photometric_bwd": 1, "ocf_smooth_fwd": 1, "ocf_smooth_bwd": 1, "ocf_gradient": 1,
+    "ocf_occ_photo_fused": 1, "ocf_pair_loss": 1,
+}
+
+
+def call(name, *args):
+    """Invoke an entry point; raise RuntimeError with the library's message on a non-zero status."""
+    global launch_count
+    code = getattr(load(), name)(*args)
+    if code != 0:
+        raise RuntimeError("ocflow_b200.%s failed: %s (code %d)" % (name, error_string(code), code))
+    launch_count += KERNELS_PER_CALL.get(name, 0)
+    return 0

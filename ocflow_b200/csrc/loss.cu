@@ -1,0 +1,398 @@
+// Occlusion-weighted photometric (Charbonnier), edge-aware smoothness and supervised losses, fp32.
+//
+// Replaces models/model.py:27-46 (robust_l1, photometric_error), :53-114 (gradient, first/second
+// order smoothness), utils.py:8-18 (charbonnier_loss) and the loss assembly of
+// general_step_occ_aware (models/model.py:379-407).  Every kernel is a single streaming pass: per-thread
+// fp32 partials -> warp shuffle -> one double atomic per block, so the scalar losses are accumulated in
+// fp64 (the reference sums in fp32 with ATen's pairwise tree; both sit far inside the 1e-3 loss bar).
+#include "common.cuh"
+
+namespace {
+
+constexpr int LT = 256;
+
+__device__ __forceinline__ float rho(float x, float a2) { return sqrtf(fmaf(x, x, a2)); }
+
+__global__ void __launch_bounds__(LT) robust_l1_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n, float a2) {
+  const size_t stride = (size_t)gridDim.x * LT;
+  for (size_t i = (size_t)blockIdx.x * LT + threadIdx.x; i < n; i += stride) y[i] = rho(x[i], a2);
+}
+
+__global__ void __launch_bounds__(LT)
+robust_l1_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, float* __restrict__ gx, size_t n, float a2) {
+  const size_t stride = (size_t)gridDim.x * LT;
+  for (size_t i = (size_t)blockIdx.x * LT + threadIdx.x; i < n; i += stride) {
+    const float v = x[i];
+    gx[i] = gy[i] * v / rho(v, a2);
+  }
+}
+
+// one thread per pixel (b, y, x); loops the C channels.  sums: [0] sum rho*(1-occ), [1] sum (1-occ)
+__global__ void __launch_bounds__(LT)
+photometric_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ img, const float* __restrict__ occ,
+                       double* __restrict__ sums, int C, size_t HW, size_t npix, float a2) {
+  float acc[2] = {0.f, 0.f};
+  const size_t stride = (size_t)gridDim.x * LT;
+  for (size_t p = (size_t)blockIdx.x * LT + threadIdx.x; p < npix; p += stride) {
+    const size_t b = p / HW, q = p - b * HW;
+    const float vis = occ != nullptr ? 1.0f - occ[p] : 1.0f;
+    float e = 0.f;
+    const size_t base = b * C * HW + q;
+    for (int c = 0; c < C; ++c) e += rho(pred[base + c * HW] - img[base + c * HW], a2);
+    acc[0] += e * vis;
+    acc[1] += vis;
+  }
+  ocf_block_accumulate<2>(acc, sums);
+}
+
+__global__ void __launch_bounds__(LT)
+photometric_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ img, const float* __restrict__ occ,
+                       const float* __restrict__ coef, float* __restrict__ d_pred, float* __restrict__ d_img,
+                       float* __restrict__ d_occ, int C, size_t HW, size_t npix, float a2) {
+  const float k0 = coef[0], k1 = coef[1];
+  const size_t stride = (size_t)gridDim.x * LT;
+  for (size_t p = (size_t)blockIdx.x * LT + threadIdx.x; p < npix; p += stride) {
+    const size_t b = p / HW, q = p - b * HW;
+    const float vis = occ != nullptr ? 1.0f - occ[p] : 1.0f;
+    const size_t base = b * C * HW + q;
+    float e = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float d = pred[base + c * HW] - img[base + c * HW];
+      const float r = rho(d, a2);
+      e += r;
+      const float gd = k0 * vis * d / r;
+      if (d_pred != nullptr) d_pred[base + c * HW] = gd;
+      if (d_img != nullptr) d_img[base + c * HW] = -gd;
+    }
+    // d/d occ of  k0*sum rho*(1-occ) + k1*sum(1-occ)
+    if (d_occ != nullptr) d_occ[p] = -(k0 * e + k1);
+  }
+}
+
+// ---- smoothness ---------------------------------------------------------------------------------
+// order 1: w = exp(-mean_c (a*(I[p+1]-I[p]))^2), term = w * sum_cf rho(F[p+1]-F[p])            (model.py:93-101)
+// order 2: w = exp(-mean_c (a*(I[p+2]-I[p]))^2), term = w * sum_cf rho((F[p+2]-F[p+1])-(F[p+1]-F[p]))  (:103-114)
+// `step` is the element distance of one pixel along the direction (1 for x, W for y).
+struct EdgeTerm {
+  float w;   // edge weight
+  float r;   // sum over flow channels of rho
+};
+
+__device__ __forceinline__ EdgeTerm edge_term(const float* __restrict__ ib, const float* __restrict__ fb, size_t q, size_t step,
+                                              int Ci, int Cf, size_t HW, int order, float ae, float a2) {
+  float s = 0.f;
+  for (int c = 0; c < Ci; ++c) {
+    const float d = ae * (ib[c * HW + q + order * step] - ib[c * HW + q]);
+    s = fmaf(d, d, s);
+  }
+  EdgeTerm t;
+  t.w = expf(-s / (float)Ci);
+  t.r = 0.f;
+  for (int c = 0; c < Cf; ++c) {
+    const float* f = fb + c * HW + q;
+    const float d = order == 1 ? f[step] - f[0] : (f[2 * step] - f[step]) - (f[step] - f[0]);
+    t.r += rho(d, a2);
+  }
+  return t;
+}
+
+__global__ void __launch_bounds__(LT)
+smooth_fwd_kernel(const float* __restrict__ img, const float* __restrict__ flow, double* __restrict__ sums, int Ci, int Cf, int H,
+                  int W, size_t npix, int order, float ae, float a2) {
+  const size_t HW = (size_t)H * W;
+  float acc[2] = {0.f, 0.f};
+  const size_t stride = (size_t)gridDim.x * LT;
+  for (size_t p = (size_t)blockIdx.x * LT + threadIdx.x; p < npix; p += stride) {
+    const size_t b = p / HW, q = p - b * HW;
+    const int y = (int)(q / W), x = (int)(q - (size_t)y * W);
+    const float* ib = img + b * Ci * HW;
+    const float* fb = flow + b * Cf * HW;
+    if (x + order < W) { const EdgeTerm t = edge_term(ib, fb, q, 1, Ci, Cf, HW, order, ae, a2); acc[0] += t.w * t.r; }
+    if (y + order < H) { const EdgeTerm t = edge_term(ib, fb, q, W, Ci, Cf, HW, order, ae, a2); acc[1] += t.w * t.r; }
+  }
+  ocf_block_accumulate<2>(acc, sums);
+}
+
+// Backward as a scatter of each edge's contribution (atomics on d_flow / d_img, zeroed by the entry point).
+__device__ __forceinline__ void edge_bwd(const float* __restrict__ ib, const float* __restrict__ fb, float* __restrict__ dib,
+                                         float* __restrict__ dfb, size_t q, size_t step, int Ci, int Cf, size_t HW, int order,
+                                         float ae, float a2, float k) {
+  float s = 0.f;
+  for (int c = 0; c < Ci; ++c) {
+    const float d = ae * (ib[c * HW + q + order * step] - ib[c * HW + q]);
+    s = fmaf(d, d, s);
+  }
+  const float w = expf(-s / (float)Ci);
+  float r = 0.f;
+  for (int c = 0; c < Cf; ++c) {
+    const float* f = fb + c * HW + q;
+    const float d = order == 1 ? f[step] - f[0] : (f[2 * step] - f[step]) - (f[step] - f[0]);
+    const float rr = rho(d, a2);
+    r += rr;
+    if (dfb != nullptr) {
+      const float t = k * w * d / rr;
+      float* df = dfb + c * HW + q;
+      if (order == 1) {
+        atomicAdd(df + step, t);
+        atomicAdd(df, -t);
+      } else {
+        atomicAdd(df + 2 * step, t);
+        atomicAdd(df + step, -2.f * t);
+        atomicAdd(df, t);
+      }
+    }
+  }
+  if (dib != nullptr) {
+    // d w / d dI_c = w * (-2 a^2 / Ci) * dI_c
+    const float kk = k * r * w * (-2.f * ae * ae / (float)Ci);
+    for (int c = 0; c < Ci; ++c) {
+      const float dI = ib[c * HW + q + order * step] - ib[c * HW + q];
+      const float t = kk * dI;
+      atomicAdd(dib + c * HW + q + order * step, t);
+      atomicAdd(dib + c * HW + q, -t);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(LT)
+smooth_bwd_kernel(const float* __restrict__ img, const float* __restrict__ flow, const float* __restrict__ coef,
+                  float* __restrict__ d_img, float* __restrict__ d_flow, int Ci, int Cf, int H, int W, size_t npix, int order,
+                  float ae, float a2) {
+  const size_t HW = (size_t)H * W;
+  const float kx = coef[0], ky = coef[1];
+  const size_t stride = (size_t)gridDim.x * LT;
+  for (size_t p = (size_t)blockIdx.x * LT + threadIdx.x; p < npix; p += stride) {
+    const size_t b = p / HW, q = p - b * HW;
+    const int y = (int)(q / W), x = (int)(q - (size_t)y * W);
+    const float* ib = img + b * Ci * HW;
+    const float* fb = flow + b * Cf * HW;
+    float* dib = d_img != nullptr ? d_img + b * Ci * HW : nullptr;
+    float* dfb = d_flow != nullptr ? d_flow + b * Cf * HW : nullptr;
+    if (x + order < W) edge_bwd(ib, fb, dib, dfb, q, 1, Ci, Cf, HW, order, ae, a2, kx);
+    if (y + order < H) edge_bwd(ib, fb, dib, dfb, q, W, Ci, Cf, HW, order, ae, a2, ky);
+  }
+}
+
+__global__ void __launch_bounds__(LT)
+gradient_kernel(const float* __restrict__ img, float* __restrict__ dx, float* __restrict__ dy, int H, int W, int s, size_t n) {
+  // n = B*C*H*W ; dx [.., H, W-s], dy [.., H-s, W]
+  const size_t stride = (size_t)gridDim.x * LT;
+  for (size_t i = (size_t)blockIdx.x * LT + threadIdx.x; i < n; i += stride) {
+    const int x = (int)(i % W);
+    const size_t row = i / W;
+    const int y = (int)(row % H);
+    const size_t plane = row / H;
+    const float v = img[i];
+    if (x + s < W) dx[(plane * H + y) * (size_t)(W - s) + x] = img[i + s] - v;
+    if (y + s < H) dy[(plane * (size_t)(H - s) + y) * W + x] = img[i + (size_t)s * W] - v;
+  }
+}
+
+// ---- fused occlusion-aware photometric pass -----------------------------------------------------
+__global__ void __launch_bounds__(LT)
+occ_photo_fused_kernel(const float* __restrict__ img1, const float* __restrict__ img2, const float* __restrict__ flow,
+                       const float* __restrict__ range, const float* __restrict__ flow_gt, const float* __restrict__ occ_gt,
+                       double* __restrict__ sums, float* __restrict__ dflow, float* __restrict__ warped, int C, int H, int W,
+                       size_t npix, float a2) {
+  const size_t HW = (size_t)H * W;
+  float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float fw = (float)(W - 1), fh = (float)(H - 1);
+  const float dw = (float)max(W - 1, 1), dh = (float)max(H - 1, 1);
+  const size_t stride = (size_t)gridDim.x * LT;
+  for (size_t p = (size_t)blockIdx.x * LT + threadIdx.x; p < npix; p += stride) {
+    const size_t b = p / HW, q = p - b * HW;
+    const int y = (int)(q / W), x = (int)(q - (size_t)y * W);
+    const float u = flow[(b * 2) * HW + q], v = flow[(b * 2 + 1) * HW + q];
+    // align_corners=True coordinates, reference op order (models/model.py:211-212 + ATen unnormalize)
+    float ix = __fmul_rn(__fdiv_rn(__fadd_rn(__fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn((float)x, u)), dw), 1.0f), 1.0f), 2.0f), fw);
+    float iy = __fmul_rn(__fdiv_rn(__fadd_rn(__fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn((float)y, v)), dh), 1.0f), 1.0f), 2.0f), fh);
+    if (!(ix > -2147483648.0f && ix < 2147483520.0f)) ix = -100.f;
+    if (!(iy > -2147483648.0f && iy < 2147483520.0f)) iy = -100.f;
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const int x0 = (int)fx0, y0 = (int)fy0;
+    const float wx1 = ix - fx0, wx0 = (fx0 + 1.f) - ix, wy1 = iy - fy0, wy0 = (fy0 + 1.f) - iy;
+    const bool vx0 = x0 >= 0 && x0 < W, vx1 = x0 + 1 >= 0 && x0 + 1 < W;
+    const bool vy0 = y0 >= 0 && y0 < H, vy1 = y0 + 1 >= 0 && y0 + 1 < H;
+    const bool vnw = vx0 && vy0, vne = vx1 && vy0, vsw = vx0 && vy1, vse = vx1 && vy1;
+    const size_t onw = vnw ? (size_t)y0 * W + x0 : 0, one = vne ? (size_t)y0 * W + x0 + 1 : 0;
+    const size_t osw = vsw ? (size_t)(y0 + 1) * W + x0 : 0, ose = vse ? (size_t)(y0 + 1) * W + x0 + 1 : 0;
+    const float occ = range != nullptr ? 1.0f - fminf(fmaxf(range[p], 0.f), 1.f) : 0.f;
+    const float vis = 1.0f - occ;
+    float e = 0.f, gx = 0.f, gy = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float* ip = img2 + (b * C + c) * HW;
+      const float a = vnw ? ip[onw] : 0.f, bb = vne ? ip[one] : 0.f, cc = vsw ? ip[osw] : 0.f, dd = vse ? ip[ose] : 0.f;
+      float s = 0.f;
+      s = fmaf(a, wx0 * wy0, s); s = fmaf(bb, wx1 * wy0, s); s = fmaf(cc, wx0 * wy1, s); s = fmaf(dd, wx1 * wy1, s);
+      if (warped != nullptr) warped[(b * C + c) * HW + q] = s;
+      const float d = s - img1[(b * C + c) * HW + q];
+      const float r = rho(d, a2);
+      e += r;
+      const float gr = d / r;  // rho'
+      gx = fmaf(gr, (bb - a) * wy0 + (dd - cc) * wy1, gx);
+      gy = fmaf(gr, (cc - a) * wx0 + (dd - bb) * wx1, gy);
+    }
+    acc[0] += e * vis; acc[1] += vis; acc[2] += e * occ; acc[3] += occ;
+    if (dflow != nullptr) {
+      // align_corners=True chain factor: (W-1)/2 * 2/max(W-1,1)
+      dflow[(b * 2) * HW + q] = gx * vis * (0.5f * fw) * (2.0f / dw);
+      dflow[(b * 2 + 1) * HW + q] = gy * vis * (0.5f * fh) * (2.0f / dh);
+    }
+    if (flow_gt != nullptr) {
+      const float du = u - flow_gt[(b * 2) * HW + q], dv = v - flow_gt[(b * 2 + 1) * HW + q];
+      acc[4] += du * du + dv * dv;
+    }
+    if (occ_gt != nullptr) {
+      // F.binary_cross_entropy(input=occ_gt, target=occ_pred)  -- swapped on purpose, models/model.py:407
+      const float pin = occ_gt[p];
+      const float lp = fmaxf(logf(pin), -100.f), l1p = fmaxf(logf(1.0f - pin), -100.f);
+      acc[5] += -(occ * lp + (1.0f - occ) * l1p);
+    }
+  }
+  ocf_block_accumulate<6>(acc, sums);
+}
+
+// ---- supervised pair losses ---------------------------------------------------------------------
+__global__ void __launch_bounds__(LT)
+pair_loss_kernel(const float* __restrict__ a, const float* __restrict__ b, double* __restrict__ sum, float* __restrict__ grad,
+                 size_t n, int kind) {
+  float acc[1] = {0.f};
+  const size_t stride = (size_t)gridDim.x * LT;
+  for (size_t i = (size_t)blockIdx.x * LT + threadIdx.x; i < n; i += stride) {
+    const float p = a[i], t = b[i];
+    float l, g;
+    if (kind == 0) {        // L1
+      const float d = p - t;
+      l = fabsf(d);
+      g = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+    } else if (kind == 1) { // squared error
+      const float d = p - t;
+      l = d * d;
+      g = 2.f * d;
+    } else {                // BCE(p, t) with ATen's -100 clamp on the logs
+      const float lp = fmaxf(logf(p), -100.f), l1p = fmaxf(logf(1.0f - p), -100.f);
+      const float bce = -(t * lp + (1.0f - t) * l1p);
+      // ATen binary_cross_entropy_backward: (p - t) / max((1-p)*p, 1e-12)
+      const float dbce = (p - t) / fmaxf((1.0f - p) * p, 1e-12f);
+      if (kind == 2) { l = bce; g = dbce; }
+      else {                // focal, gamma = 2: (1-exp(-bce))^2 * bce     (occlusion_model.py:55-62)
+        const float pt = expf(-bce), om = 1.0f - pt;
+        l = om * om * bce;
+        g = (2.f * om * pt * bce + om * om) * dbce;
+      }
+    }
+    acc[0] += l;
+    if (grad != nullptr) grad[i] = g;
+  }
+  ocf_block_accumulate<1>(acc, sum);
+}
+
+inline unsigned stream_grid(size_t n) {
+  size_t blocks = (n + LT - 1) / LT;
+  const size_t cap = (size_t)OCF_SM_COUNT * 8;  // 8 resident 256-thread CTAs per SM
+  if (blocks > cap) blocks = cap;
+  return (unsigned)(blocks ? blocks : 1);
+}
+
+}  // namespace
+
+extern "C" int ocf_robust_l1_fwd(const float* x, float* y, long long n, float alpha, ocf_stream_t stream) {
+  OCF_REQUIRE_PTR(x); OCF_REQUIRE_PTR(y);
+  OCF_REQUIRE(n > 0, OCF_ESHAPE);
+  robust_l1_fwd_kernel<<<stream_grid((size_t)n), LT, 0, ocf_cast_stream(stream)>>>(x, y, (size_t)n, alpha * alpha);
+  return ocf_launch_status();
+}
+
+extern "C" int ocf_robust_l1_bwd(const float* grad_y, const float* x, float* grad_x, long long n, float alpha, ocf_stream_t stream) {
+  OCF_REQUIRE_PTR(grad_y); OCF_REQUIRE_PTR(x); OCF_REQUIRE_PTR(grad_x);
+  OCF_REQUIRE(n > 0, OCF_ESHAPE);
+  robust_l1_bwd_kernel<<<stream_grid((size_t)n), LT, 0, ocf_cast_stream(stream)>>>(grad_y, x, grad_x, (size_t)n, alpha * alpha);
+  return ocf_launch_status();
+}
+
+extern "C" int ocf_photometric_fwd(const float* pred, const float* img, const float* occ, double* sums, int B, int C, int H, int W,
+                                   float alpha, ocf_stream_t stream) {
+  OCF_REQUIRE_PTR(pred); OCF_REQUIRE_PTR(img); OCF_REQUIRE_PTR(sums);
+  OCF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, OCF_ESHAPE);
+  cudaStream_t s = ocf_cast_stream(stream);
+  cudaError_t e = cudaMemsetAsync(sums, 0, 2 * sizeof(double), s);
+  if (e != cudaSuccess) return (int)e;
+  const size_t HW = (size_t)H * W, npix = HW * B;
+  photometric_fwd_kernel<<<stream_grid(npix), LT, 0, s>>>(pred, img, occ, sums, C, HW, npix, alpha * alpha);
+  return ocf_launch_status();
+}
+
+extern "C" int ocf_photometric_bwd(const float* pred, const float* img, const float* occ, const float* coef, float* d_pred,
+                                   float* d_img, float* d_occ, int B, int C, int H, int W, float alpha, ocf_stream_t stream) {
+  OCF_REQUIRE_PTR(pred); OCF_REQUIRE_PTR(img); OCF_REQUIRE_PTR(coef);
+  OCF_REQUIRE(d_pred != nullptr || d_img != nullptr || d_occ != nullptr, OCF_ENULL);
+  OCF_REQUIRE(d_occ == nullptr || occ != nullptr, OCF_ENULL);
+  OCF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, OCF_ESHAPE);
+  const size_t HW = (size_t)H * W, npix = HW * B;
+  photometric_bwd_kernel<<<stream_grid(npix), LT, 0, ocf_cast_stream(stream)>>>(pred, img, occ, coef, d_pred, d_img, d_occ, C, HW,
+                                                                                npix, alpha * alpha);
+  return ocf_launch_status();
+}
+
+extern "C" int ocf_smooth_fwd(const float* img, const float* flow, double* sums, int B, int Ci, int Cf, int H, int W, int order,
+                              float alpha_edge, float alpha_rho, ocf_stream_t stream) {
+  OCF_REQUIRE_PTR(img); OCF_REQUIRE_PTR(flow); OCF_REQUIRE_PTR(sums);
+  OCF_REQUIRE(B > 0 && Ci > 0 && Cf > 0 && H > 0 && W > 0, OCF_ESHAPE);
+  OCF_REQUIRE(order == 1 || order == 2, OCF_EUNSUPPORTED);
+  cudaStream_t s = ocf_cast_stream(stream);
+  cudaError_t e = cudaMemsetAsync(sums, 0, 2 * sizeof(double), s);
+  if (e != cudaSuccess) return (int)e;
+  const size_t npix = (size_t)B * H * W;
+  smooth_fwd_kernel<<<stream_grid(npix), LT, 0, s>>>(img, flow, sums, Ci, Cf, H, W, npix, order, alpha_edge, alpha_rho * alpha_rho);
+  return ocf_launch_status();
+}
+
+extern "C" int ocf_smooth_bwd(const float* img, const float* flow, const float* coef, float* d_img, float* d_flow, int B, int Ci,
+                              int Cf, int H, int W, int order, float alpha_edge, float alpha_rho, ocf_stream_t stream) {
+  OCF_REQUIRE_PTR(img); OCF_REQUIRE_PTR(flow); OCF_REQUIRE_PTR(coef);
+  OCF_REQUIRE(d_img != nullptr || d_flow != nullptr, OCF_ENULL);
+  OCF_REQUIRE(B > 0 && Ci > 0 && Cf > 0 && H > 0 && W > 0, OCF_ESHAPE);
+  OCF_REQUIRE(order == 1 || order == 2, OCF_EUNSUPPORTED);
+  cudaStream_t s = ocf_cast_stream(stream);
+  const size_t npix = (size_t)B * H * W;
+  cudaError_t e;
+  if (d_img != nullptr && (e = cudaMemsetAsync(d_img, 0, sizeof(float) * npix * Ci, s)) != cudaSuccess) return (int)e;
+  if (d_flow != nullptr && (e = cudaMemsetAsync(d_flow, 0, sizeof(float) * npix * Cf, s)) != cudaSuccess) return (int)e;
+  smooth_bwd_kernel<<<stream_grid(npix), LT, 0, s>>>(img, flow, coef, d_img, d_flow, Ci, Cf, H, W, npix, order, alpha_edge,
+                                                     alpha_rho * alpha_rho);
+  return ocf_launch_status();
+}
+
+extern "C" int ocf_gradient(const float* img, float* dx, float* dy, int B, int C, int H, int W, int stride, ocf_stream_t stream) {
+  OCF_REQUIRE_PTR(img); OCF_REQUIRE_PTR(dx); OCF_REQUIRE_PTR(dy);
+  OCF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, OCF_ESHAPE);
+  OCF_REQUIRE(stride >= 1 && stride < H && stride < W, OCF_ESHAPE);
+  const size_t n = (size_t)B * C * H * W;
+  gradient_kernel<<<stream_grid(n), LT, 0, ocf_cast_stream(stream)>>>(img, dx, dy, H, W, stride, n);
+  return ocf_launch_status();
+}
+
+extern "C" int ocf_occ_photo_fused(const float* img1, const float* img2, const float* flow, const float* range_map,
+                                   const float* flow_gt, const float* occ_gt, double* sums, float* dflow_unit, float* warped_out,
+                                   int B, int C, int H, int W, float alpha, ocf_stream_t stream) {
+  OCF_REQUIRE_PTR(img1); OCF_REQUIRE_PTR(img2); OCF_REQUIRE_PTR(flow); OCF_REQUIRE_PTR(sums);
+  OCF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, OCF_ESHAPE);
+  cudaStream_t s = ocf_cast_stream(stream);
+  cudaError_t e = cudaMemsetAsync(sums, 0, 8 * sizeof(double), s);
+  if (e != cudaSuccess) return (int)e;
+  const size_t npix = (size_t)B * H * W;
+  occ_photo_fused_kernel<<<stream_grid(npix), LT, 0, s>>>(img1, img2, flow, range_map, flow_gt, occ_gt, sums, dflow_unit, warped_out,
+                                                          C, H, W, npix, alpha * alpha);
+  return ocf_launch_status();
+}
+
+extern "C" int ocf_pair_loss(const float* a, const float* b, double* sum_out, float* grad, long long n, int kind, ocf_stream_t stream) {
+  OCF_REQUIRE_PTR(a); OCF_REQUIRE_PTR(b); OCF_REQUIRE_PTR(sum_out);
+  OCF_REQUIRE(n > 0, OCF_ESHAPE);
+  OCF_REQUIRE(kind >= 0 && kind <= 3, OCF_EUNSUPPORTED);
+  cudaStream_t s = ocf_cast_stream(stream);
+  cudaError_t e = cudaMemsetAsync(sum_out, 0, sizeof(double), s);
+  if (e != cudaSuccess) return (int)e;
+  pair_loss_kernel<<<stream_grid((size_t)n), LT, 0, s>>>(a, b, sum_out, grad, (size_t)n, kind);
+  return ocf_launch_status();
+}

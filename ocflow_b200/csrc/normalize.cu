@@ -1,0 +1,215 @@
+// Feature normalisation forward/backward (reference models/networks/correlation_layer.py:42-82).
+//
+// A "group" is the set of elements one var_mean reduces over: one sample of one tensor
+// (moments_across_channels) or one channel of one sample.  With moments_across_images the reference
+// averages the per-group means and variances of ALL tensors to a single scalar pair (:66-68) -- the
+// variance is the mean of per-group biased variances, not the pooled variance.
+//
+// forward : (1) partial sums per group in fp64 atomics, (2) one tiny finalize CTA turning sums into the
+//           applied {mean, inv_std} per group, (3) streaming apply y = (x - mean) * inv_std.
+// backward: same three steps with sum(g), sum(g*x): the reference does not detach the statistics, so
+//           d x_i = g_i*r + A + Bc*(x_i - mu_group(i)).
+//
+// Workspace layout (floats, caller-owned; NG = T*B*G groups, G = 1 or C):
+//   stats: [0, 4NG)  2NG doubles  sum(x), sum(x^2) per group           (fwd scratch)
+//          [4NG,6NG) {mean, var} per group
+//          [6NG,8NG) {mean_applied, inv_std_applied} per group
+//   red  : [0, 4NG)  2NG doubles  sum(g), sum(g*x) per group           (bwd scratch)
+//          [4NG,7NG) {r', A, Bc} per group
+#include "common.cuh"
+
+namespace {
+
+constexpr int NT = 256;
+constexpr int MAX_T = 8;
+
+struct PtrPack {
+  const float* in[MAX_T];
+  const float* in2[MAX_T];
+  float* out[MAX_T];
+};
+
+// grid: (chunks, NG).  Group gidx = (t*B + b)*G + gc covers `glen` contiguous floats.
+__global__ void __launch_bounds__(NT)
+group_sums_kernel(PtrPack pk, int B, int G, size_t glen, double* __restrict__ sums, bool with_second) {
+  const int gidx = blockIdx.y;
+  const int t = gidx / (B * G), rem = gidx - t * (B * G);
+  const float* x = pk.in[t] + (size_t)rem * glen;
+  const float* w = with_second ? pk.in2[t] + (size_t)rem * glen : nullptr;
+  // fwd: s0 = sum x, s1 = sum x^2 ; bwd (with_second: x = grad, w = input): s0 = sum g, s1 = sum g*x
+  float acc[2] = {0.f, 0.f};
+  const size_t per = (glen + gridDim.x - 1) / gridDim.x;
+  const size_t lo = (size_t)blockIdx.x * per, hi = min(glen, lo + per);
+  for (size_t i = lo + threadIdx.x; i < hi; i += NT) {
+    const float a = x[i];
+    const float bb = with_second ? w[i] : a;
+    acc[0] += a;
+    acc[1] = fmaf(a, bb, acc[1]);
+  }
+  ocf_block_accumulate<2>(acc, sums + 2 * (size_t)gidx);
+}
+
+__global__ void norm_finalize_fwd_kernel(float* __restrict__ stats, int NG, double inv_len, int flags) {
+  const double* sums = reinterpret_cast<const double*>(stats);
+  float* grp = stats + 4 * (size_t)NG;
+  float* app = stats + 6 * (size_t)NG;
+  __shared__ double sm[2];
+  if (threadIdx.x == 0) { sm[0] = 0.0; sm[1] = 0.0; }
+  __syncthreads();
+  double lm = 0.0, lv = 0.0;
+  for (int g = threadIdx.x; g < NG; g += blockDim.x) {
+    const double m = sums[2 * g] * inv_len;
+    double v = sums[2 * g + 1] * inv_len - m * m;
+    if (v < 0.0) v = 0.0;
+    grp[2 * g] = (float)m;
+    grp[2 * g + 1] = (float)v;
+    lm += m; lv += v;
+  }
+  lm = ocf_warp_sum(lm); lv = ocf_warp_sum(lv);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&sm[0], lm); atomicAdd(&sm[1], lv); }
+  __syncthreads();
+  const bool across = flags & OCF_NORM_ACROSS_IMAGES;
+  const float gm = (float)(sm[0] / NG), gv = (float)(sm[1] / NG);
+  for (int g = threadIdx.x; g < NG; g += blockDim.x) {
+    const float m = across ? gm : grp[2 * g];
+    const float v = across ? gv : grp[2 * g + 1];
+    app[2 * g] = (flags & OCF_NORM_CENTER) ? m : 0.f;
+    app[2 * g + 1] = (flags & OCF_NORM_NORMALIZE) ? 1.0f / sqrtf(v + 1e-16f) : 1.f;
+  }
+}
+
+// y = (x - m) * r per group.  grid: (chunks, NG)
+__global__ void __launch_bounds__(NT)
+norm_apply_kernel(PtrPack pk, int B, int G, size_t glen, const float* __restrict__ app, bool vec) {
+  const int gidx = blockIdx.y;
+  const int t = gidx / (B * G), rem = gidx - t * (B * G);
+  const float* x = pk.in[t] + (size_t)rem * glen;
+  float* y = pk.out[t] + (size_t)rem * glen;
+  const float m = app[2 * gidx], r = app[2 * gidx + 1];
+  if (vec) {
+    const size_t n4 = glen / 4;
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < n4; i += (size_t)gridDim.x * NT) {
+      float4 v = reinterpret_cast<const float4*>(x)[i];
+      v.x = (v.x - m) * r; v.y = (v.y - m) * r; v.z = (v.z - m) * r; v.w = (v.w - m) * r;
+      reinterpret_cast<float4*>(y)[i] = v;
+    }
+  } else {
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < glen; i += (size_t)gridDim.x * NT) y[i] = (x[i] - m) * r;
+  }
+}
+
+__global__ void norm_finalize_bwd_kernel(const float* __restrict__ stats, float* __restrict__ red, int NG, double glen, int flags) {
+  const double* sums = reinterpret_cast<const double*>(red);  // sum g, sum g*x per group
+  const float* grp = stats + 4 * (size_t)NG;
+  const float* app = stats + 6 * (size_t)NG;
+  float* co = red + 4 * (size_t)NG;
+  const bool across = flags & OCF_NORM_ACROSS_IMAGES, nz = flags & OCF_NORM_NORMALIZE, ce = flags & OCF_NORM_CENTER;
+  __shared__ double sm[2];
+  if (threadIdx.x == 0) { sm[0] = 0.0; sm[1] = 0.0; }
+  __syncthreads();
+  double sg = 0.0, sgx = 0.0;
+  for (int g = threadIdx.x; g < NG; g += blockDim.x) { sg += sums[2 * g]; sgx += sums[2 * g + 1]; }
+  sg = ocf_warp_sum(sg); sgx = ocf_warp_sum(sgx);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&sm[0], sg); atomicAdd(&sm[1], sgx); }
+  __syncthreads();
+  for (int g = threadIdx.x; g < NG; g += blockDim.x) {
+    const double m = app[2 * g], r = app[2 * g + 1];           // applied mean (0 when !center), inv_std (1 when !normalize)
+    const double Sg = across ? sm[0] : sums[2 * g];
+    const double Sgx = across ? sm[1] : sums[2 * g + 1];
+    const double cnt = across ? glen * NG : glen;               // elements the statistics average over
+    // y = (x - m) * r ;  dL/dm = -r*Sg (center) ; dL/dr = Sgx - m*Sg (normalize) ; r = (v+eps)^-1/2
+    const double dLdm = ce ? -r * Sg : 0.0;
+    const double dLdv = nz ? (Sgx - m * Sg) * (-0.5 * r * r * r) : 0.0;
+    co[3 * g] = (float)r;
+    co[3 * g + 1] = (float)(dLdm / cnt);
+    co[3 * g + 2] = (float)(dLdv * 2.0 / cnt);                  // multiplies (x_i - mu_group(i))
+  }
+  (void)grp;
+}
+
+__global__ void __launch_bounds__(NT)
+norm_bwd_apply_kernel(PtrPack pk, int B, int G, size_t glen, const float* __restrict__ stats, const float* __restrict__ red, int NG) {
+  const int gidx = blockIdx.y;
+  const int t = gidx / (B * G), rem = gidx - t * (B * G);
+  const float* g = pk.in[t] + (size_t)rem * glen;
+  const float* x = pk.in2[t] + (size_t)rem * glen;
+  float* dx = pk.out[t] + (size_t)rem * glen;
+  const float mu = stats[4 * (size_t)NG + 2 * gidx];
+  const float* co = red + 4 * (size_t)NG + 3 * (size_t)gidx;
+  const float r = co[0], A = co[1], Bc = co[2];
+  for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < glen; i += (size_t)gridDim.x * NT)
+    dx[i] = fmaf(g[i], r, fmaf(Bc, x[i] - mu, A));
+}
+
+int chunks_for(size_t glen, int NG) {
+  // aim at ~4 CTAs per SM overall, each with at least 2048 elements
+  long long want = (4LL * OCF_SM_COUNT + NG - 1) / NG;
+  long long maxc = (long long)((glen + 2047) / 2048);
+  if (want > maxc) want = maxc;
+  if (want < 1) want = 1;
+  if (want > 65535) want = 65535;
+  return (int)want;
+}
+
+}  // namespace
+
+extern "C" int ocf_normalize_fwd(const float* const* xs, float* const* ys, int T, int B, int C, int H, int W, int flags, float* stats,
+                                 ocf_stream_t stream) {
+  OCF_REQUIRE_PTR(xs); OCF_REQUIRE_PTR(ys); OCF_REQUIRE_PTR(stats);
+  OCF_REQUIRE(T > 0 && T <= MAX_T, OCF_EUNSUPPORTED);
+  OCF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, OCF_ESHAPE);
+  OCF_REQUIRE((flags & ~15) == 0, OCF_EUNSUPPORTED);
+  OCF_REQUIRE((reinterpret_cast<uintptr_t>(stats) & 7u) == 0, OCF_EALIGN);
+  PtrPack pk;
+  bool vec = true;
+  for (int t = 0; t < T; ++t) {
+    OCF_REQUIRE_PTR(xs[t]); OCF_REQUIRE_PTR(ys[t]);
+    pk.in[t] = xs[t]; pk.in2[t] = nullptr; pk.out[t] = ys[t];
+    vec = vec && ocf_aligned16(xs[t]) && ocf_aligned16(ys[t]);
+  }
+  const int G = (flags & OCF_NORM_ACROSS_CHANNELS) ? 1 : C;
+  const size_t glen = (size_t)(G == 1 ? C : 1) * H * W;
+  const long long NGll = (long long)T * B * G;
+  OCF_REQUIRE(NGll <= 65535, OCF_EUNSUPPORTED);
+  const int NG = (int)NGll;
+  vec = vec && (glen % 4 == 0);
+  cudaStream_t s = ocf_cast_stream(stream);
+  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * NG, s);
+  if (e != cudaSuccess) return (int)e;
+  const int chunks = chunks_for(glen, NG);
+  group_sums_kernel<<<dim3(chunks, NG), NT, 0, s>>>(pk, B, G, glen, reinterpret_cast<double*>(stats), false);
+  if (int st = ocf_launch_status()) return st;
+  norm_finalize_fwd_kernel<<<1, 256, 0, s>>>(stats, NG, 1.0 / (double)glen, flags);
+  if (int st = ocf_launch_status()) return st;
+  norm_apply_kernel<<<dim3(chunks, NG), NT, 0, s>>>(pk, B, G, glen, stats + 6 * (size_t)NG, vec);
+  return ocf_launch_status();
+}
+
+extern "C" int ocf_normalize_bwd(const float* const* grad_ys, const float* const* xs, float* const* grad_xs, int T, int B, int C, int H,
+                                 int W, int flags, const float* stats, float* red, ocf_stream_t stream) {
+  OCF_REQUIRE_PTR(grad_ys); OCF_REQUIRE_PTR(xs); OCF_REQUIRE_PTR(grad_xs); OCF_REQUIRE_PTR(stats); OCF_REQUIRE_PTR(red);
+  OCF_REQUIRE(T > 0 && T <= MAX_T, OCF_EUNSUPPORTED);
+  OCF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, OCF_ESHAPE);
+  OCF_REQUIRE((flags & ~15) == 0, OCF_EUNSUPPORTED);
+  OCF_REQUIRE((reinterpret_cast<uintptr_t>(red) & 7u) == 0, OCF_EALIGN);
+  PtrPack pk;
+  for (int t = 0; t < T; ++t) {
+    OCF_REQUIRE_PTR(grad_ys[t]); OCF_REQUIRE_PTR(xs[t]); OCF_REQUIRE_PTR(grad_xs[t]);
+    pk.in[t] = grad_ys[t]; pk.in2[t] = xs[t]; pk.out[t] = grad_xs[t];
+  }
+  const int G = (flags & OCF_NORM_ACROSS_CHANNELS) ? 1 : C;
+  const size_t glen = (size_t)(G == 1 ? C : 1) * H * W;
+  const long long NGll = (long long)T * B * G;
+  OCF_REQUIRE(NGll <= 65535, OCF_EUNSUPPORTED);
+  const int NG = (int)NGll;
+  cudaStream_t s = ocf_cast_stream(stream);
+  cudaError_t e = cudaMemsetAsync(red, 0, sizeof(double) * 2 * NG, s);
+  if (e != cudaSuccess) return (int)e;
+  const int chunks = chunks_for(glen, NG);
+  group_sums_kernel<<<dim3(chunks, NG), NT, 0, s>>>(pk, B, G, glen, reinterpret_cast<double*>(red), true);
+  if (int st = ocf_launch_status()) return st;
+  norm_finalize_bwd_kernel<<<1, 256, 0, s>>>(stats, red, NG, (double)glen, flags);
+  if (int st = ocf_launch_status()) return st;
+  norm_bwd_apply_kernel<<<dim3(chunks, NG), NT, 0, s>>>(pk, B, G, glen, stats, red, NG);
+  return ocf_launch_status();
+}

@@ -1,0 +1,316 @@
+// Bilinear backward warp (forward gather, backward scatter) and range-map forward splat, fp32 NCHW.
+//
+// Replaces the reference's 11 `warp` / `backwarp` bodies (meshgrid on the CPU + H2D copy + ~15 ATen
+// launches + F.grid_sample, e.g. utils.py:20-58, cost_volume_flow_net.py:121-151) and
+// compute_range_map (models/model.py:243-305: 4 x nonzero host syncs + scatter_add_).
+//
+// Coordinates follow the reference + ATen op order exactly, with FMA contraction suppressed:
+//   g  = 2*(x+u)/max(W-1,1) - 1                      (utils.py:43-44)
+//   ix = ((g+1)/2)*(W-1)          align_corners=True  (ATen GridSampler.h grid_sampler_unnormalize)
+//   ix = ((g+1)*W-1)/2            align_corners=False
+// so align_corners=False samples at (x+u)*W/(W-1) - 0.5, the reference's quirk.
+#include "common.cuh"
+
+namespace {
+
+struct Taps {
+  int x0, y0;          // north-west tap
+  float wx0, wx1, wy0, wy1;
+  bool vx0, vx1, vy0, vy1;
+};
+
+__device__ __forceinline__ float unnormalize(float v, int size, int denom, bool align) {
+  // v: pixel + flow.  reference normalisation then ATen un-normalisation, one rounding per op.
+  float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, v), (float)denom), 1.0f);
+  float r;
+  if (align) r = __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.0f), 2.0f), (float)(size - 1));
+  else r = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.0f), (float)size), 1.0f), 2.0f);
+  // ATen compute_coordinates -> safe_downgrade_to_int_range
+  if (!(r > -2147483648.0f && r < 2147483520.0f)) r = -100.0f;
+  return r;
+}
+
+__device__ __forceinline__ Taps make_taps(float ix, float iy, int H, int W) {
+  Taps t;
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  t.x0 = (int)fx0;
+  t.y0 = (int)fy0;
+  t.wx1 = ix - fx0;            // weight of the east taps
+  t.wx0 = (fx0 + 1.0f) - ix;   // weight of the west taps  (ATen: ix_se - ix)
+  t.wy1 = iy - fy0;
+  t.wy0 = (fy0 + 1.0f) - iy;
+  t.vx0 = t.x0 >= 0 && t.x0 < W;
+  t.vx1 = t.x0 + 1 >= 0 && t.x0 + 1 < W;
+  t.vy0 = t.y0 >= 0 && t.y0 < H;
+  t.vy1 = t.y0 + 1 >= 0 && t.y0 + 1 < H;
+  return t;
+}
+
+__device__ __forceinline__ float cover_of(const Taps& t) {
+  float m = 0.f;
+  if (t.vx0 && t.vy0) m += t.wx0 * t.wy0;
+  if (t.vx1 && t.vy0) m += t.wx1 * t.wy0;
+  if (t.vx0 && t.vy1) m += t.wx0 * t.wy1;
+  if (t.vx1 && t.vy1) m += t.wx1 * t.wy1;
+  return m;
+}
+
+// utils.py:54-55: mask<0.9999 -> 0 ; mask>0 -> 1
+__device__ __forceinline__ float mask_of(const Taps& t) { return cover_of(t) < 0.9999f ? 0.f : 1.f; }
+
+constexpr int WARP_THREADS = 256;
+
+// grid: (ceil(HW/256), channel slabs, B)
+__global__ void __launch_bounds__(WARP_THREADS)
+warp_fwd_kernel(const float* __restrict__ img, const float* __restrict__ flow, const float* __restrict__ occ,
+                float* __restrict__ out, int C, int H, int W, int slab, int flags, float scale) {
+  const int pix = blockIdx.x * WARP_THREADS + threadIdx.x;
+  const int HW = H * W;
+  if (pix >= HW) return;
+  const int y = pix / W, x = pix - y * W;
+  const int b = blockIdx.z;
+  const bool align = flags & OCF_WARP_ALIGN_CORNERS;
+  const float u = __fmul_rn(__ldg(flow + ((size_t)b * 2) * HW + pix), scale);
+  const float v = __fmul_rn(__ldg(flow + ((size_t)b * 2 + 1) * HW + pix), scale);
+  const float ix = unnormalize(__fadd_rn((float)x, u), W, max(W - 1, 1), align);
+  const float iy = unnormalize(__fadd_rn((float)y, v), H, max(H - 1, 1), align);
+  const Taps t = make_taps(ix, iy, H, W);
+  float mul = 1.f;
+  if (flags & OCF_WARP_IS_MASK) mul = mask_of(t);
+  if (occ != nullptr) mul *= __ldg(occ + (size_t)b * HW + pix);
+  const float wnw = t.wx0 * t.wy0, wne = t.wx1 * t.wy0, wsw = t.wx0 * t.wy1, wse = t.wx1 * t.wy1;
+  const bool vnw = t.vx0 && t.vy0, vne = t.vx1 && t.vy0, vsw = t.vx0 && t.vy1, vse = t.vx1 && t.vy1;
+  // clamp the tap offsets so that even dropped taps form a valid address (never dereferenced)
+  const int onw = vnw ? t.y0 * W + t.x0 : 0, one = vne ? t.y0 * W + t.x0 + 1 : 0;
+  const int osw = vsw ? (t.y0 + 1) * W + t.x0 : 0, ose = vse ? (t.y0 + 1) * W + t.x0 + 1 : 0;
+  const int c_begin = blockIdx.y * slab, c_end = min(C, c_begin + slab);
+  const float* ip = img + ((size_t)b * C + c_begin) * HW;
+  float* op = out + ((size_t)b * C + c_begin) * HW + pix;
+#pragma unroll 4
+  for (int c = c_begin; c < c_end; ++c, ip += HW, op += HW) {
+    float r = 0.f;
+    if (vnw) r = fmaf(__ldg(ip + onw), wnw, r);
+    if (vne) r = fmaf(__ldg(ip + one), wne, r);
+    if (vsw) r = fmaf(__ldg(ip + osw), wsw, r);
+    if (vse) r = fmaf(__ldg(ip + ose), wse, r);
+    *op = r * mul;
+  }
+}
+
+// Backward.  d_img is a scatter (red.global.add.f32, zeroed by the caller entry point); d_flow / d_occ are
+// per-pixel and accumulated across channel slabs with one atomic per slab (plain store when 1 slab).
+// Neighbouring lanes usually hit neighbouring taps; merging the east tap of lane l with the west
+// tap of lane l+1 in registers halves the atomics (warp-aggregated scatter).
+__global__ void __launch_bounds__(WARP_THREADS)
+warp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ img, const float* __restrict__ flow,
+                const float* __restrict__ occ, float* __restrict__ d_img, float* __restrict__ d_flow,
+                float* __restrict__ d_occ, int C, int H, int W, int slab, int nslabs, int flags, float scale) {
+  const int pix = blockIdx.x * WARP_THREADS + threadIdx.x;
+  const int HW = H * W;
+  const bool active = pix < HW;
+  const int pixc = active ? pix : HW - 1;
+  const int y = pixc / W, x = pixc - y * W;
+  const int b = blockIdx.z;
+  const bool align = flags & OCF_WARP_ALIGN_CORNERS;
+  const float u = __fmul_rn(__ldg(flow + ((size_t)b * 2) * HW + pixc), scale);
+  const float v = __fmul_rn(__ldg(flow + ((size_t)b * 2 + 1) * HW + pixc), scale);
+  const float ix = unnormalize(__fadd_rn((float)x, u), W, max(W - 1, 1), align);
+  const float iy = unnormalize(__fadd_rn((float)y, v), H, max(H - 1, 1), align);
+  const Taps t = make_taps(ix, iy, H, W);
+  float mul = active ? 1.f : 0.f;
+  if (flags & OCF_WARP_IS_MASK) mul *= mask_of(t);
+  float occv = 1.f;
+  if (occ != nullptr) occv = __ldg(occ + (size_t)b * HW + pixc);
+  const float gmul = mul * occv;  // d out / d sample
+  const float wnw = t.wx0 * t.wy0, wne = t.wx1 * t.wy0, wsw = t.wx0 * t.wy1, wse = t.wx1 * t.wy1;
+  const bool vnw = t.vx0 && t.vy0, vne = t.vx1 && t.vy0, vsw = t.vx0 && t.vy1, vse = t.vx1 && t.vy1;
+  const int onw = vnw ? t.y0 * W + t.x0 : 0, one = vne ? t.y0 * W + t.x0 + 1 : 0;
+  const int osw = vsw ? (t.y0 + 1) * W + t.x0 : 0, ose = vse ? (t.y0 + 1) * W + t.x0 + 1 : 0;
+
+  // lane-neighbour merge plan (channel independent): my west taps can absorb the previous lane's east
+  // taps when they are the same address and both valid.
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int prev_one = __shfl_up_sync(full, vne ? one : -1, 1);
+  const int prev_ose = __shfl_up_sync(full, vse ? ose : -1, 1);
+  const bool take_n = lane > 0 && vnw && prev_one == onw;   // I add prev lane's NE into my NW
+  const bool take_s = lane > 0 && vsw && prev_ose == osw;
+  const bool give_n = __shfl_down_sync(full, (int)take_n, 1) && lane < 31;  // my NE is absorbed by next lane
+  const bool give_s = __shfl_down_sync(full, (int)take_s, 1) && lane < 31;
+
+  const int c_begin = blockIdx.y * slab, c_end = min(C, c_begin + slab);
+  const float* ip = img + ((size_t)b * C + c_begin) * HW;
+  const float* gp = gout + ((size_t)b * C + c_begin) * HW + pixc;
+  float* dp = d_img != nullptr ? d_img + ((size_t)b * C + c_begin) * HW : nullptr;
+  float gx = 0.f, gy = 0.f, go = 0.f;
+  const bool need_vals = d_flow != nullptr || d_occ != nullptr;
+  for (int c = c_begin; c < c_end; ++c, ip += HW, gp += HW) {
+    const float graw = active ? __ldg(gp) : 0.f;
+    const float g = graw * gmul;
+    if (need_vals) {
+      const float a = vnw ? __ldg(ip + onw) : 0.f, bb = vne ? __ldg(ip + one) : 0.f;
+      const float cc = vsw ? __ldg(ip + osw) : 0.f, dd = vse ? __ldg(ip + ose) : 0.f;
+      // ATen grid_sampler_2d_backward: gix -= nw*(iy_se-iy) ; += ne*(iy_sw-iy) ; -= sw*(iy-iy_ne) ; += se*(iy-iy_nw)
+      gx += g * ((bb - a) * t.wy0 + (dd - cc) * t.wy1);
+      gy += g * ((cc - a) * t.wx0 + (dd - bb) * t.wx1);
+      if (d_occ != nullptr) go += graw * mul * (a * wnw + bb * wne + cc * wsw + dd * wse);
+    }
+    if (dp != nullptr) {
+      float cnw = g * wnw, cne = g * wne, csw = g * wsw, cse = g * wse;
+      const float pn = __shfl_up_sync(full, cne, 1), ps = __shfl_up_sync(full, cse, 1);
+      if (take_n) cnw += pn;
+      if (take_s) csw += ps;
+      if (vnw) atomicAdd(dp + onw, cnw);
+      if (vne && !give_n) atomicAdd(dp + one, cne);
+      if (vsw) atomicAdd(dp + osw, csw);
+      if (vse && !give_s) atomicAdd(dp + ose, cse);
+      dp += HW;
+    }
+  }
+  if (!active) return;
+  if (d_flow != nullptr) {
+    // chain: ATen multiplies by (W-1)/2 resp. W/2, the reference's normalisation by 2/max(W-1,1)
+    const float mx = (align ? 0.5f * (float)(W - 1) : 0.5f * (float)W) * (2.0f / (float)max(W - 1, 1)) * scale;
+    const float my = (align ? 0.5f * (float)(H - 1) : 0.5f * (float)H) * (2.0f / (float)max(H - 1, 1)) * scale;
+    float* fx = d_flow + ((size_t)b * 2) * HW + pix;
+    if (nslabs == 1) { fx[0] = gx * mx; fx[HW] = gy * my; }
+    else { atomicAdd(fx, gx * mx); atomicAdd(fx + HW, gy * my); }
+  }
+  if (d_occ != nullptr) {
+    float* po = d_occ + (size_t)b * HW + pix;
+    if (nslabs == 1) *po = go; else atomicAdd(po, go);
+  }
+}
+
+// ---- range map ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+range_map_kernel(const float* __restrict__ flow, float* __restrict__ range, int H, int W) {
+  const int pix = blockIdx.x * 256 + threadIdx.x;
+  const int HW = H * W;
+  const bool active = pix < HW;
+  const int pixc = active ? pix : HW - 1;
+  const int y = pixc / W, x = pixc - y * W;
+  const int b = blockIdx.y;
+  const float ex = __fadd_rn((float)x, __ldg(flow + ((size_t)b * 2) * HW + pixc));      // flow_to_warp, model.py:223-241
+  const float ey = __fadd_rn((float)y, __ldg(flow + ((size_t)b * 2 + 1) * HW + pixc));
+  const float fx0 = floorf(ex), fy0 = floorf(ey);
+  const float ox = ex - fx0, oy = ey - fy0;
+  // guard the float->int conversion (the reference's .to(int32) is undefined for huge values)
+  const bool sane = active && fabsf(fx0) < 1.0e9f && fabsf(fy0) < 1.0e9f;
+  const int x0 = sane ? (int)fx0 : -10, y0 = sane ? (int)fy0 : -10;
+  const bool vx0 = x0 >= 0 && x0 < W, vx1 = x0 + 1 >= 0 && x0 + 1 < W;
+  const bool vy0 = y0 >= 0 && y0 < H, vy1 = y0 + 1 >= 0 && y0 + 1 < H;
+  float w00 = (1.f - ox) * (1.f - oy), w10 = ox * (1.f - oy), w01 = (1.f - ox) * oy, w11 = ox * oy;
+  const int o00 = (vx0 && vy0) ? y0 * W + x0 : -1, o10 = (vx1 && vy0) ? y0 * W + x0 + 1 : -1;
+  const int o01 = (vx0 && vy1) ? (y0 + 1) * W + x0 : -1, o11 = (vx1 && vy1) ? (y0 + 1) * W + x0 + 1 : -1;
+  // warp-aggregated scatter: fold the previous lane's east taps into my west taps when they coincide
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int p10 = __shfl_up_sync(full, o10, 1), p11 = __shfl_up_sync(full, o11, 1);
+  const float q10 = __shfl_up_sync(full, w10, 1), q11 = __shfl_up_sync(full, w11, 1);
+  const bool take0 = lane > 0 && o00 >= 0 && p10 == o00;
+  const bool take1 = lane > 0 && o01 >= 0 && p11 == o01;
+  if (take0) w00 += q10;
+  if (take1) w01 += q11;
+  const bool give0 = __shfl_down_sync(full, (int)take0, 1) && lane < 31;
+  const bool give1 = __shfl_down_sync(full, (int)take1, 1) && lane < 31;
+  float* r = range + (size_t)b * HW;
+  if (o00 >= 0) atomicAdd(r + o00, w00);
+  if (o10 >= 0 && !give0) atomicAdd(r + o10, w10);
+  if (o01 >= 0) atomicAdd(r + o01, w01);
+  if (o11 >= 0 && !give1) atomicAdd(r + o11, w11);
+}
+
+__global__ void __launch_bounds__(256)
+occ_from_range_kernel(const float* __restrict__ range, float* __restrict__ occ, size_t n) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) occ[i] = 1.0f - fminf(fmaxf(range[i], 0.0f), 1.0f);  // model.py:391
+}
+
+__global__ void __launch_bounds__(256)
+flow_to_warp_kernel(const float* __restrict__ flow, float* __restrict__ out, int H, int W, size_t n2) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;  // index over B*H*W*2 (channels-last flow)
+  if (i >= n2) return;
+  const size_t p = i >> 1;
+  const int comp = (int)(i & 1);
+  const int x = (int)(p % W), y = (int)((p / W) % H);
+  out[i] = __fadd_rn(comp == 0 ? (float)x : (float)y, flow[i]);
+}
+
+int pick_slab(int C, int HW, int B) {
+  // enough CTAs to fill 148 SMs a few times over, but at most 16 channels of coordinate reuse per thread
+  const long long pix_blocks = ((long long)HW + WARP_THREADS - 1) / WARP_THREADS * B;
+  int slab = C;
+  while (slab > 4 && pix_blocks * ((C + slab - 1) / slab) < 4LL * OCF_SM_COUNT) slab = (slab + 1) / 2;
+  if (slab > 32) slab = 32;
+  return slab < 1 ? 1 : slab;
+}
+
+}  // namespace
+
+extern "C" int ocf_warp_fwd(const float* img, const float* flow, const float* occ, float* out, int B, int C, int H, int W,
+                            int flags, float scale, ocf_stream_t stream) {
+  OCF_REQUIRE_PTR(img); OCF_REQUIRE_PTR(flow); OCF_REQUIRE_PTR(out);
+  OCF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, OCF_ESHAPE);
+  OCF_REQUIRE((long long)H * W < (1LL << 30) && B <= 65535, OCF_EUNSUPPORTED);
+  OCF_REQUIRE((flags & ~3) == 0, OCF_EUNSUPPORTED);
+  const int HW = H * W;
+  const int slab = pick_slab(C, HW, B);
+  const int nslabs = (C + slab - 1) / slab;
+  OCF_REQUIRE(nslabs <= 65535, OCF_EUNSUPPORTED);
+  dim3 grid((HW + WARP_THREADS - 1) / WARP_THREADS, nslabs, B);
+  warp_fwd_kernel<<<grid, WARP_THREADS, 0, ocf_cast_stream(stream)>>>(img, flow, occ, out, C, H, W, slab, flags, scale);
+  return ocf_launch_status();
+}
+
+extern "C" int ocf_warp_bwd(const float* grad_out, const float* img, const float* flow, const float* occ, float* d_img,
+                            float* d_flow, float* d_occ, int B, int C, int H, int W, int flags, float scale,
+                            ocf_stream_t stream) {
+  OCF_REQUIRE_PTR(grad_out); OCF_REQUIRE_PTR(img); OCF_REQUIRE_PTR(flow);
+  OCF_REQUIRE(d_img != nullptr || d_flow != nullptr || d_occ != nullptr, OCF_ENULL);
+  OCF_REQUIRE(d_occ == nullptr || occ != nullptr, OCF_ENULL);
+  OCF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, OCF_ESHAPE);
+  OCF_REQUIRE((long long)H * W < (1LL << 30) && B <= 65535, OCF_EUNSUPPORTED);
+  OCF_REQUIRE((flags & ~3) == 0, OCF_EUNSUPPORTED);
+  cudaStream_t s = ocf_cast_stream(stream);
+  const int HW = H * W;
+  const int slab = pick_slab(C, HW, B);
+  const int nslabs = (C + slab - 1) / slab;
+  OCF_REQUIRE(nslabs <= 65535, OCF_EUNSUPPORTED);
+  cudaError_t e;
+  if (d_img != nullptr && (e = cudaMemsetAsync(d_img, 0, sizeof(float) * (size_t)B * C * HW, s)) != cudaSuccess) return (int)e;
+  if (nslabs > 1) {
+    if (d_flow != nullptr && (e = cudaMemsetAsync(d_flow, 0, sizeof(float) * (size_t)B * 2 * HW, s)) != cudaSuccess) return (int)e;
+    if (d_occ != nullptr && (e = cudaMemsetAsync(d_occ, 0, sizeof(float) * (size_t)B * HW, s)) != cudaSuccess) return (int)e;
+  }
+  dim3 grid((HW + WARP_THREADS - 1) / WARP_THREADS, nslabs, B);
+  warp_bwd_kernel<<<grid, WARP_THREADS, 0, s>>>(grad_out, img, flow, occ, d_img, d_flow, d_occ, C, H, W, slab, nslabs, flags, scale);
+  return ocf_launch_status();
+}
+
+extern "C" int ocf_range_map(const float* flow, float* range_out, float* occ_out, int B, int H, int W, ocf_stream_t stream) {
+  OCF_REQUIRE_PTR(flow); OCF_REQUIRE_PTR(range_out);
+  OCF_REQUIRE(B > 0 && H > 0 && W > 0, OCF_ESHAPE);
+  OCF_REQUIRE((long long)H * W < (1LL << 30) && B <= 65535, OCF_EUNSUPPORTED);
+  cudaStream_t s = ocf_cast_stream(stream);
+  const int HW = H * W;
+  cudaError_t e = cudaMemsetAsync(range_out, 0, sizeof(float) * (size_t)B * HW, s);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid((HW + 255) / 256, B);
+  range_map_kernel<<<grid, 256, 0, s>>>(flow, range_out, H, W);
+  if (int st = ocf_launch_status()) return st;
+  if (occ_out != nullptr) {
+    const size_t n = (size_t)B * HW;
+    occ_from_range_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(range_out, occ_out, n);
+  }
+  return ocf_launch_status();
+}
+
+extern "C" int ocf_flow_to_warp(const float* flow_bhw2, float* out_bhw2, int B, int H, int W, ocf_stream_t stream) {
+  OCF_REQUIRE_PTR(flow_bhw2); OCF_REQUIRE_PTR(out_bhw2);
+  OCF_REQUIRE(B > 0 && H > 0 && W > 0, OCF_ESHAPE);
+  const size_t n2 = (size_t)B * H * W * 2;
+  OCF_REQUIRE(n2 < (1ULL << 39), OCF_EUNSUPPORTED);
+  flow_to_warp_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, ocf_cast_stream(stream)>>>(flow_bhw2, out_bhw2, H, W, n2);
+  return ocf_launch_status();
+}

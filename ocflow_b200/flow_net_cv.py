@@ -1,0 +1,106 @@
+"""FlowNetCV on the B200 hot path -- host-side mirror of models/networks/cost_volume_flow_net.py:22-246.
+
+Same constructor (`FlowNetCV(displacement=4)`), same parameter names/shapes and creation order (so a reference
+checkpoint loads unchanged and `torch.manual_seed(s)` yields the reference's initial weights), same forward contract:
+`forward(x[B,6,H,W]) -> (flow1 [B,2,H,W] pixels, flow_l2 [B,2,H/4,W/4] quarter-res pixels)`.
+
+Per pyramid level the reference runs warp -> normalize_features -> compute_cost_volume -> LeakyReLU as ~1000 ATen
+launches; here it is 5 launches of our kernels (warp with the `up_flow*scale` folded in, 3-kernel normalisation,
+correlation with the LeakyReLU fused).  The convolution stacks stay on cuDNN (out of scope).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+# (name, in, out, stride) of the feature pyramid, in the reference's creation order (:30-47)
+_ENCODER = (
+    ("conv1a", 3, 16, 2), ("conv1aa", 16, 16, 1), ("conv1b", 16, 16, 1),
+    ("conv2a", 16, 32, 2), ("conv2aa", 32, 32, 1), ("conv2b", 32, 32, 1),
+    ("conv3a", 32, 64, 2), ("conv3aa", 64, 64, 1), ("conv3b", 64, 64, 1),
+    ("conv4a", 64, 96, 2), ("conv4aa", 96, 96, 1), ("conv4b", 96, 96, 1),
+    ("conv5a", 96, 128, 2), ("conv5aa", 128, 128, 1), ("conv5b", 128, 128, 1),
+    ("conv6aa", 128, 196, 2), ("conv6a", 196, 196, 1), ("conv6b", 196, 196, 1),
+)
+_PYRAMID = {1: ("conv1a", "conv1aa", "conv1b"), 2: ("conv2a", "conv2aa", "conv2b"), 3: ("conv3a", "conv3aa", "conv3b"),
+            4: ("conv4a", "conv4aa", "conv4b"), 5: ("conv5a", "conv5aa", "conv5b"), 6: ("conv6aa", "conv6a", "conv6b")}
+_LEVEL_FEAT = {6: 0, 5: 128, 4: 96, 3: 64, 2: 32}       # channels of c1 concatenated at the level
+_DENSE_OUT = (128, 128, 96, 64, 32)
+# flow is predicted in units of pixels/20 at full resolution: the warp at level l uses 20 / 2**l
+_WARP_SCALE = {5: 0.625, 4: 1.25, 3: 2.5, 2: 5.0}
+_CONTEXT = ((128, 1), (128, 2), (128, 4), (96, 8), (64, 16), (32, 1))  # (out channels, dilation)
+
+
+def _conv_block(cin, cout, stride=1, dilation=1):
+    return nn.Sequential(nn.Conv2d(cin, cout, 3, stride=stride, padding=dilation, dilation=dilation, bias=True), nn.LeakyReLU(0.1))
+
+
+class FlowNetCV(nn.Module):
+    def __init__(self, displacement=4):
+        super().__init__()
+        for name, cin, cout, stride in _ENCODER:
+            setattr(self, name, _conv_block(cin, cout, stride))
+        self.leakyRELU = nn.LeakyReLU(0.1)
+        self.displacement = int(displacement)
+        nd = (2 * self.displacement + 1) ** 2
+        for lvl in (6, 5, 4, 3, 2):
+            width = nd + (_LEVEL_FEAT[lvl] + 4 if lvl < 6 else 0)
+            for i, cout in enumerate(_DENSE_OUT):
+                setattr(self, "conv%d_%d" % (lvl, i), _conv_block(width, cout))
+                width += cout
+            setattr(self, "predict_flow%d" % lvl, nn.Conv2d(width, 2, 3, 1, 1, bias=True))
+            setattr(self, "deconv%d" % lvl, nn.ConvTranspose2d(2, 2, 4, 2, 1, bias=True))
+            if lvl > 2:
+                setattr(self, "upfeat%d" % lvl, nn.ConvTranspose2d(width, 2, 4, 2, 1, bias=True))
+        cin = width
+        for i, (cout, dil) in enumerate(_CONTEXT):
+            setattr(self, "dc_conv%d" % (i + 1), _conv_block(cin, cout, 1, dil))
+            cin = cout
+        self.dc_conv7 = nn.Conv2d(cin, 2, 3, 1, 1, bias=True)
+
+    # reference API: FlowNetCV.warp(img, flow) (cost_volume_flow_net.py:121-151, align_corners=False)
+    def warp(self, img, flow):
+        return ops.warp(img, flow, align_corners=False)
+
+    @staticmethod
+    def normalize(feature_list, **kw):
+        return ops.normalize_features(feature_list, **kw)
+
+    def pyramid(self, im):
+        feats = {}
+        t = im
+        for lvl in range(1, 7):
+            for name in _PYRAMID[lvl]:
+                t = getattr(self, name)(t)
+            feats[lvl] = t
+        return feats
+
+    def _level(self, lvl, c1, c2, up_flow, up_feat):
+        if lvl < 6:
+            c2 = ops.warp(c2, up_flow, align_corners=False, flow_scale=_WARP_SCALE[lvl])
+        c1, c2 = ops.normalize_features([c1, c2])
+        corr = ops.cost_volume(c1, c2, self.displacement, leaky_slope=0.1)
+        x = corr if lvl == 6 else torch.cat((corr, c1, up_flow, up_feat), 1)
+        for i in range(5):
+            x = torch.cat((getattr(self, "conv%d_%d" % (lvl, i))(x), x), 1)
+        flow = getattr(self, "predict_flow%d" % lvl)(x)
+        return x, flow
+
+    def forward(self, x):
+        if x.dim() != 4 or x.shape[1] != 6:
+            raise ValueError("FlowNetCV expects [B,6,H,W] (two RGB images), got %s" % (tuple(x.shape),))
+        p1 = self.pyramid(x[:, :3])
+        p2 = self.pyramid(x[:, 3:])
+        up_flow = up_feat = None
+        for lvl in (6, 5, 4, 3, 2):
+            feat, flow = self._level(lvl, p1[lvl], p2[lvl], up_flow, up_feat)
+            if lvl > 2:
+                up_flow = getattr(self, "deconv%d" % lvl)(flow)
+                up_feat = getattr(self, "upfeat%d" % lvl)(feat)
+        t = feat
+        for i in range(1, 7):
+            t = getattr(self, "dc_conv%d" % i)(t)
+        flow2 = flow + self.dc_conv7(t)
+        flow1 = F.interpolate(flow2, scale_factor=4, mode="bilinear", align_corners=True) * 20
+        return flow1, flow2 * 5.0

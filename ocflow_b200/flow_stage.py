@@ -1,0 +1,131 @@
+"""FlowStageModel on the B200 hot path -- mirror of models/model.py:155-509 for model == 'pwc'.
+
+Same `hparams` dict keys and defaults (models/model.py:161-170), same method names, argument meaning and return
+tuples: `general_step` (:315-341), `general_step_occ` (:343-364), `general_step_occ_aware` (:366-409),
+`training_step` (:411-436, minus the TensorBoard writes, which need a Lightning logger), `configure_optimizers`
+(:508-509).  It is a plain nn.Module: pytorch_lightning is neither needed nor imported.
+
+The occlusion-aware step collapses warp(img2, flow) -> range map -> occlusion mask -> photometric(occ) ->
+photometric(1-occ) -> mse -> bce (≈120 ATen launches and 4 host syncs in the reference) into 2 kernels.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.optim import Adam
+
+from . import ops
+from .flow_net_cv import FlowNetCV
+
+
+class FlowStageModel(nn.Module):
+    def __init__(self, hparams):
+        super().__init__()
+        self.hparams = dict(hparams)
+        self.lr = hparams["learning_rate"]
+        self.photo_weight = hparams.get("photo_weight", 1.0)
+        self.smooth1_weight = hparams.get("smooth1_weight", 0.0)
+        self.smooth2_weight = hparams.get("smooth2_weight", 1.0)
+        self.with_occ = hparams.get("with_occ", False)
+        self.log_every_n_steps = hparams.get("log_every_n_steps", 20)
+        self.occ_aware = hparams.get("occ_aware", False)
+        self.displacement = hparams.get("displacement", 4)
+        model = hparams.get("model", "simple")
+        self.model = model
+        if model != "pwc":
+            # the other reference networks are plain conv stacks without correlation/warping
+            raise ValueError("Unsupported model: %s (ocflow_b200 implements the 'pwc' hot path)" % model)
+        self.flow_pred = FlowNetCV(displacement=self.displacement)
+        self.last_scalars = {}
+
+    def forward(self, x):
+        return self.flow_pred(x)
+
+    # ---- reference helper methods (models/model.py:191-305) ----
+    def warp(self, img, flow):
+        return ops.warp(img, flow, align_corners=True)
+
+    def flow_to_warp(self, flow):
+        return ops.flow_to_warp(flow)
+
+    def compute_range_map(self, flow):
+        return ops.range_map(flow)
+
+    @property
+    def is_cuda(self):
+        return next(self.parameters()).is_cuda
+
+    def save_state_dict(self, path):
+        torch.save(self.state_dict(), path)
+
+    # ---- steps ----
+    @staticmethod
+    def _unpack(batch):
+        if len(batch) == 2:
+            imgs, flow = batch
+            return imgs, flow, None
+        if len(batch) == 3:
+            return batch
+        raise ValueError("Not supported dataset")
+
+    def _smoothness(self, img1, flow_l2):
+        img1_l2 = F.interpolate(img1, scale_factor=0.25, mode="bilinear", align_corners=True)
+        smooth1 = ops.smoothness_loss(img1_l2, flow_l2, 1)
+        smooth2 = ops.smoothness_loss(img1_l2, flow_l2, 2)
+        return smooth1, smooth2
+
+    def general_step(self, batch, batch_idx, mode):
+        imgs, flow, _ = self._unpack(batch)
+        img1, img2 = imgs[:, 0:3], imgs[:, 3:6]
+        flow_pred, flow_l2 = self(imgs)
+        photo, _, flow_error, _ = ops.occ_photo_fused(img1, img2, flow_pred, None, flow, None)
+        # without an occlusion map the fused pass computes sum(rho)/(3*N): identical to torch.mean for 3 channels
+        smooth1, smooth2 = self._smoothness(img1, flow_l2)
+        return photo, smooth1, smooth2, flow_error
+
+    def general_step_occ(self, batch, batch_idx, mode):
+        imgs, flow, occ = batch
+        img1, img2 = imgs[:, 0:3], imgs[:, 3:6]
+        flow_pred, flow_l2 = self(imgs)
+        img_warped = ops.warp(img2, flow_pred, align_corners=True)
+        photo = ops.photometric_error(img_warped, img1, occ)
+        smooth1, smooth2 = self._smoothness(img1, flow_l2)
+        flow_error = ops.pair_loss(flow_pred, flow, ops.PAIR_MSE)
+        return photo, smooth1, smooth2, flow_error
+
+    def general_step_occ_aware(self, batch, batch_idx, mode):
+        imgs, flow, occ = self._unpack(batch)
+        img1, img2 = imgs[:, 0:3], imgs[:, 3:6]
+        flow_pred, flow_l2 = self(imgs)
+        with torch.no_grad():
+            back_flow_pred, _ = self(torch.cat((img2, img1), dim=1))
+            range_map = ops.range_map(back_flow_pred)
+        photo, photo_occ, flow_error, occ_error = ops.occ_photo_fused(img1, img2, flow_pred, range_map, flow, occ)
+        smooth1, smooth2 = self._smoothness(img1, flow_l2)
+        if occ is not None:
+            return photo, smooth1, smooth2, flow_error, photo_occ, occ_error
+        return photo, smooth1, smooth2, flow_error, photo_occ
+
+    def _losses(self, batch, batch_idx, mode):
+        if not self.occ_aware:
+            if not self.with_occ:
+                return self.general_step(batch, batch_idx, mode)
+            return self.general_step_occ(batch, batch_idx, mode)
+        return self.general_step_occ_aware(batch, batch_idx, mode)
+
+    def training_step(self, batch, batch_idx):
+        losses = self._losses(batch, batch_idx, "train")
+        photo, smooth1, smooth2 = losses[0], losses[1], losses[2]
+        loss = self.photo_weight * photo + self.smooth1_weight * smooth1 + self.smooth2_weight * smooth2
+        names = ("photometric", "smooth1", "smooth2", "flow_error", "photometric_occ", "occ_error")
+        self.last_scalars = {"train_" + n: v.detach() for n, v in zip(names, losses)}
+        return loss
+
+    def validation_step(self, batch, batch_idx):
+        with torch.no_grad():
+            losses = self._losses(batch, batch_idx, "val")
+        return self.photo_weight * losses[0] + self.smooth1_weight * losses[1] + self.smooth2_weight * losses[2]
+
+    test_step = validation_step
+
+    def configure_optimizers(self):
+        return Adam(self.parameters(), self.lr)

@@ -1,0 +1,438 @@
+"""torch.autograd wrappers over the C ABI (include/ocflow_b200.h).  CUDA fp32 tensors only.
+
+PyTorch is plumbing here: it owns device memory and streams and records the autograd graph; every
+forward and backward below is one call into libocflow_b200.so on torch's current CUDA stream.
+There is no CPU path: a non-CUDA or non-fp32 tensor raises TypeError.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+NORM_NORMALIZE, NORM_CENTER, NORM_ACROSS_CHANNELS, NORM_ACROSS_IMAGES = 1, 2, 4, 8
+WARP_ALIGN_CORNERS, WARP_IS_MASK = 1, 2
+
+
+def _req(t, name, dims=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor, got %s" % (name, type(t).__name__))
+    if not t.is_cuda:
+        raise TypeError("%s must be a CUDA tensor: ocflow_b200 has no CPU path (got device %s)" % (name, t.device))
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32 (got %s)" % (name, t.dtype))
+    if dims is not None and t.dim() != dims:
+        raise ValueError("%s must have %d dimensions (got shape %s)" % (name, dims, tuple(t.shape)))
+    return t.contiguous()
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# -------------------------------------------------------------------------------------------------
+# cost volume
+# -------------------------------------------------------------------------------------------------
+class _CostVolume(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f1, f2, d, slope):
+        B, C, H, W = f1.shape
+        nd = 2 * d + 1
+        out = torch.empty((B, nd * nd, H, W), device=f1.device, dtype=torch.float32)
+        with torch.cuda.device_of(f1):
+            _lib.call("ocf_corr_fwd", _p(f1), _p(f2), _p(out), B, C, H, W, d, 0, float(slope), None, _stream())
+        ctx.d, ctx.slope = d, float(slope)
+        if slope != 1.0:
+            ctx.save_for_backward(f1, f2, out)
+        else:
+            ctx.save_for_backward(f1, f2)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        saved = ctx.saved_tensors
+        f1, f2 = saved[0], saved[1]
+        act = saved[2] if len(saved) == 3 else None
+        B, C, H, W = f1.shape
+        g = g.contiguous()
+        need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        df1 = torch.empty_like(f1) if need1 else None
+        df2 = torch.empty_like(f2) if need2 else None
+        if need1 or need2:
+            with torch.cuda.device_of(f1):
+                _lib.call("ocf_corr_bwd", _p(g), _p(act), _p(f1), _p(f2), _p(df1), _p(df2), B, C, H, W, ctx.d, 0, ctx.slope, _stream())
+        return df1, df2, None, None
+
+
+def cost_volume(f1, f2, max_displacement=4, leaky_slope=1.0):
+    f1 = _req(f1, "features1", 4)
+    f2 = _req(f2, "features2", 4)
+    if f1.shape != f2.shape:
+        raise ValueError("features1 and features2 must have the same shape (got %s vs %s)" % (tuple(f1.shape), tuple(f2.shape)))
+    return _CostVolume.apply(f1, f2, int(max_displacement), float(leaky_slope))
+
+
+# -------------------------------------------------------------------------------------------------
+# feature normalisation
+# -------------------------------------------------------------------------------------------------
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return arr
+
+
+class _Normalize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flags, *xs):
+        T = len(xs)
+        B, C, H, W = xs[0].shape
+        G = 1 if flags & NORM_ACROSS_CHANNELS else C
+        NG = T * B * G
+        ys = [torch.empty_like(x) for x in xs]
+        stats = torch.empty(8 * NG, device=xs[0].device, dtype=torch.float32)
+        with torch.cuda.device_of(xs[0]):
+            _lib.call("ocf_normalize_fwd", ctypes.cast(_ptr_array(xs), ctypes.c_void_p), ctypes.cast(_ptr_array(ys), ctypes.c_void_p),
+                      T, B, C, H, W, flags, _p(stats), _stream())
+        ctx.flags, ctx.NG = flags, NG
+        ctx.save_for_backward(stats, *xs)
+        return tuple(ys)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        stats, xs = ctx.saved_tensors[0], ctx.saved_tensors[1:]
+        T = len(xs)
+        B, C, H, W = xs[0].shape
+        gs = [torch.zeros_like(x) if g is None else g.contiguous() for g, x in zip(gs, xs)]
+        dxs = [torch.empty_like(x) for x in xs]
+        red = torch.empty(8 * ctx.NG, device=xs[0].device, dtype=torch.float32)
+        with torch.cuda.device_of(xs[0]):
+            _lib.call("ocf_normalize_bwd", ctypes.cast(_ptr_array(gs), ctypes.c_void_p), ctypes.cast(_ptr_array(xs), ctypes.c_void_p),
+                      ctypes.cast(_ptr_array(dxs), ctypes.c_void_p), T, B, C, H, W, ctx.flags, _p(stats), _p(red), _stream())
+        return (None,) + tuple(dxs)
+
+
+def normalize_features(feature_list, normalize=True, center=True, moments_across_channels=True, moments_across_images=True):
+    xs = [_req(f, "feature_list[%d]" % i, 4) for i, f in enumerate(feature_list)]
+    if not xs:
+        return []
+    if not (normalize or center):
+        return list(feature_list)
+    for x in xs[1:]:
+        if x.shape != xs[0].shape:
+            raise ValueError("all tensors of feature_list must share one shape")
+    flags = (NORM_NORMALIZE if normalize else 0) | (NORM_CENTER if center else 0) | \
+        (NORM_ACROSS_CHANNELS if moments_across_channels else 0) | (NORM_ACROSS_IMAGES if moments_across_images else 0)
+    return list(_Normalize.apply(flags, *xs))
+
+
+# -------------------------------------------------------------------------------------------------
+# bilinear backward warp
+# -------------------------------------------------------------------------------------------------
+class _Warp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, flow, occ, flags, scale):
+        B, C, H, W = img.shape
+        out = torch.empty_like(img)
+        with torch.cuda.device_of(img):
+            _lib.call("ocf_warp_fwd", _p(img), _p(flow), _p(occ), _p(out), B, C, H, W, flags, float(scale), _stream())
+        ctx.flags, ctx.scale, ctx.has_occ = flags, float(scale), occ is not None
+        if occ is not None:
+            ctx.save_for_backward(img, flow, occ)
+        else:
+            ctx.save_for_backward(img, flow)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        img, flow = ctx.saved_tensors[0], ctx.saved_tensors[1]
+        occ = ctx.saved_tensors[2] if ctx.has_occ else None
+        B, C, H, W = img.shape
+        g = g.contiguous()
+        need_img, need_flow = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        need_occ = ctx.has_occ and ctx.needs_input_grad[2]
+        d_img = torch.empty_like(img) if need_img else None
+        d_flow = torch.empty_like(flow) if need_flow else None
+        d_occ = torch.empty_like(occ) if need_occ else None
+        if need_img or need_flow or need_occ:
+            with torch.cuda.device_of(img):
+                _lib.call("ocf_warp_bwd", _p(g), _p(img), _p(flow), _p(occ), _p(d_img), _p(d_flow), _p(d_occ), B, C, H, W, ctx.flags,
+                          ctx.scale, _stream())
+        return d_img, d_flow, d_occ, None, None
+
+
+def warp(img, flow, align_corners=True, is_mask=False, occ=None, flow_scale=1.0):
+    img = _req(img, "img", 4)
+    flow = _req(flow, "flow", 4)
+    B, C, H, W = img.shape
+    if flow.shape != (B, 2, H, W):
+        raise ValueError("flow must be [B,2,H,W] matching img (got %s for img %s)" % (tuple(flow.shape), tuple(img.shape)))
+    if occ is not None:
+        occ = _req(occ, "occ", 4)
+        if occ.shape != (B, 1, H, W):
+            raise ValueError("occ must be [B,1,H,W]")
+    flags = (WARP_ALIGN_CORNERS if align_corners else 0) | (WARP_IS_MASK if is_mask else 0)
+    return _Warp.apply(img, flow, occ, flags, float(flow_scale))
+
+
+# -------------------------------------------------------------------------------------------------
+# range map / occlusion  (forward only: the reference calls it under no_grad, models/model.py:381-391)
+# -------------------------------------------------------------------------------------------------
+def range_map(flow, with_occlusion=False):
+    flow = _req(flow.detach(), "flow", 4)
+    B, two, H, W = flow.shape
+    if two != 2:
+        raise ValueError("flow must be [B,2,H,W]")
+    rmap = torch.empty((B, 1, H, W), device=flow.device, dtype=torch.float32)
+    occ = torch.empty_like(rmap) if with_occlusion else None
+    with torch.cuda.device_of(flow):
+        _lib.call("ocf_range_map", _p(flow), _p(rmap), _p(occ), B, H, W, _stream())
+    if with_occlusion:
+        _lib.launch_count += 1
+        return rmap, occ
+    return rmap
+
+
+def flow_to_warp(flow_bhw2):
+    flow = _req(flow_bhw2.detach(), "flow", 4)
+    B, H, W, two = flow.shape
+    if two != 2:
+        raise ValueError("flow must be [B,H,W,2]")
+    out = torch.empty_like(flow)
+    with torch.cuda.device_of(flow):
+        _lib.call("ocf_flow_to_warp", _p(flow), _p(out), B, H, W, _stream())
+    return out
+
+
+# -------------------------------------------------------------------------------------------------
+# Charbonnier / photometric
+# -------------------------------------------------------------------------------------------------
+class _RobustL1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, alpha):
+        y = torch.empty_like(x)
+        with torch.cuda.device_of(x):
+            _lib.call("ocf_robust_l1_fwd", _p(x), _p(y), x.numel(), float(alpha), _stream())
+        ctx.alpha = float(alpha)
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        gx = torch.empty_like(x)
+        g = g.contiguous()
+        with torch.cuda.device_of(x):
+            _lib.call("ocf_robust_l1_bwd", _p(g), _p(x), _p(gx), x.numel(), ctx.alpha, _stream())
+        return gx, None
+
+
+def robust_l1(x, alpha=0.001):
+    x = _req(x, "x")
+    if x.numel() == 0:
+        return torch.empty_like(x)
+    return _RobustL1.apply(x, float(alpha))
+
+
+class _Photometric(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, img, occ, alpha):
+        B, C, H, W = pred.shape
+        sums = torch.empty(2, device=pred.device, dtype=torch.float64)
+        with torch.cuda.device_of(pred):
+            _lib.call("ocf_photometric_fwd", _p(pred), _p(img), _p(occ), _p(sums), B, C, H, W, float(alpha), _stream())
+        if occ is not None:
+            den = sums[1] * 3 + 1e-16           # the literal 3 of models/model.py:43
+        else:
+            den = torch.full((), float(B * C * H * W), device=pred.device, dtype=torch.float64)
+        loss = (sums[0] / den).to(torch.float32)
+        ctx.alpha, ctx.has_occ = float(alpha), occ is not None
+        if occ is not None:
+            ctx.save_for_backward(pred, img, sums, den, occ)
+        else:
+            ctx.save_for_backward(pred, img, sums, den)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, img, sums, den = ctx.saved_tensors[:4]
+        occ = ctx.saved_tensors[4] if ctx.has_occ else None
+        B, C, H, W = pred.shape
+        g64 = g.to(torch.float64)
+        k0 = g64 / den
+        k1 = -3.0 * g64 * sums[0] / (den * den) if ctx.has_occ else torch.zeros_like(k0)
+        coef = torch.stack((k0, k1)).to(torch.float32)
+        need_pred, need_img = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        need_occ = ctx.has_occ and ctx.needs_input_grad[2]
+        d_pred = torch.empty_like(pred) if need_pred else None
+        d_img = torch.empty_like(img) if need_img else None
+        d_occ = torch.empty_like(occ) if need_occ else None
+        if need_pred or need_img or need_occ:
+            with torch.cuda.device_of(pred):
+                _lib.call("ocf_photometric_bwd", _p(pred), _p(img), _p(occ), _p(coef), _p(d_pred), _p(d_img), _p(d_occ), B, C, H, W,
+                          ctx.alpha, _stream())
+        return d_pred, d_img, d_occ, None
+
+
+def photometric_error(img_pred, img, occ=None, alpha=0.001):
+    pred = _req(img_pred, "img_pred", 4)
+    img = _req(img, "img", 4)
+    if pred.shape != img.shape:
+        raise ValueError("img_pred and img must have the same shape")
+    if occ is not None:
+        occ = _req(occ, "occ", 4)
+        if occ.shape != (pred.shape[0], 1, pred.shape[2], pred.shape[3]):
+            raise ValueError("occ must be [B,1,H,W]")
+    return _Photometric.apply(pred, img, occ, float(alpha))
+
+
+# -------------------------------------------------------------------------------------------------
+# smoothness
+# -------------------------------------------------------------------------------------------------
+class _Smooth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, flow, order, alpha_edge, alpha_rho):
+        B, Ci, H, W = img.shape
+        Cf = flow.shape[1]
+        sums = torch.empty(2, device=img.device, dtype=torch.float64)
+        with torch.cuda.device_of(img):
+            _lib.call("ocf_smooth_fwd", _p(img), _p(flow), _p(sums), B, Ci, Cf, H, W, order, float(alpha_edge), float(alpha_rho), _stream())
+        nx = float(B * Cf * H * (W - order))
+        ny = float(B * Cf * (H - order) * W)
+        ctx.cfg = (order, float(alpha_edge), float(alpha_rho), nx, ny)
+        ctx.save_for_backward(img, flow)
+        scale = torch.tensor([0.5 / nx, 0.5 / ny], device=img.device, dtype=torch.float64)
+        return (sums * scale).sum().to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        img, flow = ctx.saved_tensors
+        order, ae, ar, nx, ny = ctx.cfg
+        B, Ci, H, W = img.shape
+        Cf = flow.shape[1]
+        coef = (g.reshape(1) * torch.tensor([0.5 / nx, 0.5 / ny], device=img.device, dtype=torch.float32)).contiguous()
+        need_img, need_flow = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        d_img = torch.empty_like(img) if need_img else None
+        d_flow = torch.empty_like(flow) if need_flow else None
+        if need_img or need_flow:
+            with torch.cuda.device_of(img):
+                _lib.call("ocf_smooth_bwd", _p(img), _p(flow), _p(coef), _p(d_img), _p(d_flow), B, Ci, Cf, H, W, order, ae, ar, _stream())
+        return d_img, d_flow, None, None, None
+
+
+def smoothness_loss(img, flow, order, alpha=100.0, alpha_rho=0.001):
+    img = _req(img, "img", 4)
+    flow = _req(flow, "flow", 4)
+    if img.shape[0] != flow.shape[0] or img.shape[2:] != flow.shape[2:]:
+        raise ValueError("img and flow must share batch and spatial size")
+    if img.shape[2] <= order or img.shape[3] <= order:
+        raise ValueError("image too small for a stride-%d gradient" % order)
+    return _Smooth.apply(img, flow, int(order), float(alpha), float(alpha_rho))
+
+
+class _Gradient(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, stride):
+        B, C, H, W = img.shape
+        dx = torch.empty((B, C, H, W - stride), device=img.device, dtype=torch.float32)
+        dy = torch.empty((B, C, H - stride, W), device=img.device, dtype=torch.float32)
+        with torch.cuda.device_of(img):
+            _lib.call("ocf_gradient", _p(img), _p(dx), _p(dy), B, C, H, W, stride, _stream())
+        ctx.stride = stride
+        return dx, dy
+
+    @staticmethod
+    def backward(ctx, gdx, gdy):
+        # adjoint of a forward difference is a (negated) backward difference: plain tensor glue
+        s = ctx.stride
+        B, C, H, Wm = gdx.shape
+        W = Wm + s
+        g = gdx.new_zeros((B, C, H, W))
+        g[:, :, :, s:] += gdx
+        g[:, :, :, :-s] -= gdx
+        g[:, :, s:, :] += gdy
+        g[:, :, :-s, :] -= gdy
+        return g, None
+
+
+def gradient(img, stride=1):
+    img = _req(img, "img", 4)
+    return _Gradient.apply(img, int(stride))
+
+
+# -------------------------------------------------------------------------------------------------
+# supervised pair losses
+# -------------------------------------------------------------------------------------------------
+PAIR_L1, PAIR_MSE, PAIR_BCE, PAIR_FOCAL = 0, 1, 2, 3
+
+
+class _PairLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, kind):
+        s = torch.empty(1, device=a.device, dtype=torch.float64)
+        need = ctx.needs_input_grad[0]
+        grad = torch.empty_like(a) if need else None
+        with torch.cuda.device_of(a):
+            _lib.call("ocf_pair_loss", _p(a), _p(b), _p(s), _p(grad), a.numel(), kind, _stream())
+        ctx.n = a.numel()
+        if need:
+            ctx.save_for_backward(grad)
+        return (s[0] / a.numel()).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * (g / ctx.n), None, None
+
+
+def pair_loss(a, b, kind):
+    a = _req(a, "input")
+    b = _req(b.detach(), "target")
+    if a.shape != b.shape:
+        raise ValueError("input and target must have the same shape")
+    return _PairLoss.apply(a, b, int(kind))
+
+
+# -------------------------------------------------------------------------------------------------
+# fused occlusion-aware photometric pass (models/model.py:379-407 in one kernel)
+# -------------------------------------------------------------------------------------------------
+class _OccPhotoFused(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img1, img2, flow, rmap, flow_gt, occ_gt, alpha):
+        B, C, H, W = img1.shape
+        sums = torch.empty(8, device=img1.device, dtype=torch.float64)
+        need = ctx.needs_input_grad[2]
+        dflow = torch.empty_like(flow) if need else None
+        with torch.cuda.device_of(img1):
+            _lib.call("ocf_occ_photo_fused", _p(img1), _p(img2), _p(flow), _p(rmap), _p(flow_gt), _p(occ_gt), _p(sums), _p(dflow), None,
+                      B, C, H, W, float(alpha), _stream())
+        den_vis = sums[1] * 3 + 1e-16
+        den_occ = sums[3] * 3 + 1e-16
+        photo = (sums[0] / den_vis).to(torch.float32)
+        photo_occ = (sums[2] / den_occ).to(torch.float32)
+        mse = (sums[4] / float(B * 2 * H * W)).to(torch.float32)
+        bce = (sums[5] / float(B * H * W)).to(torch.float32)
+        if need:
+            ctx.save_for_backward(dflow, den_vis)
+        ctx.mark_non_differentiable(photo_occ, mse, bce)
+        return photo, photo_occ, mse, bce
+
+    @staticmethod
+    def backward(ctx, g_photo, g_pocc, g_mse, g_bce):
+        dflow, den_vis = ctx.saved_tensors
+        k = (g_photo.to(torch.float64) / den_vis).to(torch.float32)
+        return None, None, dflow * k, None, None, None, None
+
+
+def occ_photo_fused(img1, img2, flow, rmap=None, flow_gt=None, occ_gt=None, alpha=0.001):
+    """(photo, photo_occ, flow_mse, occ_bce) of general_step_occ_aware in one pass; grad flows to `flow` via photo only
+    (the other three are logged-only scalars in the reference, models/model.py:403-407)."""
+    img1 = _req(img1.detach(), "img1", 4)
+    img2 = _req(img2.detach(), "img2", 4)
+    flow = _req(flow, "flow", 4)
+    rmap = None if rmap is None else _req(rmap.detach(), "range_map", 4)
+    flow_gt = None if flow_gt is None else _req(flow_gt.detach(), "flow_gt", 4)
+    occ_gt = None if occ_gt is None else _req(occ_gt.detach(), "occ_gt", 4)
+    return _OccPhotoFused.apply(img1, img2, flow, rmap, flow_gt, occ_gt, float(alpha))

@@ -1,0 +1,69 @@
+"""CPU: the C-ABI library loads, exports every symbol include/ocflow_b200.h declares, and validates arguments
+before touching the GPU (no compute call is made here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, "include", "ocflow_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    decls = re.findall(r"\b(?:int|const char\*)\s+(ocf_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S)
+    return {name: [a.strip() for a in args.split(",")] if args.strip() != "void" else [] for name, args in decls}
+
+
+def test_header_declares_and_library_exports_every_symbol():
+    from ocflow_b200 import _lib
+
+    decl = _declared()
+    assert len(decl) >= 20
+    lib = _lib.load()
+    for name in decl:
+        assert hasattr(lib, name), "libocflow_b200.so does not export %s" % name
+    assert lib.ocf_abi_version() == 1
+    assert lib.ocf_build_sm() == 100
+    assert b"OCF_ENULL" in lib.ocf_error_string(-1)
+
+
+def test_ctypes_table_matches_header_arity():
+    from ocflow_b200 import _lib
+
+    decl = _declared()
+    for name, argtypes in _lib.SIGNATURES.items():
+        assert name in decl, name
+        assert len(decl[name]) == len(argtypes), "%s: header has %d args, ctypes table %d" % (name, len(decl[name]), len(argtypes))
+    known = set(_lib.SIGNATURES) | set(_lib.NOARG) | {"ocf_error_string"}
+    assert set(decl) == known, set(decl) ^ known
+
+
+def test_argument_validation_happens_before_any_launch():
+    from ocflow_b200 import _lib
+
+    lib = _lib.load()
+    one = ctypes.c_void_p(16)  # never dereferenced: validation fails first
+    assert lib.ocf_corr_fwd(None, one, one, 1, 1, 1, 1, 4, 0, 1.0, None, None) == -1
+    assert lib.ocf_corr_fwd(one, one, one, 0, 1, 1, 1, 4, 0, 1.0, None, None) == -2
+    assert lib.ocf_corr_fwd(one, one, one, 1, 1, 1, 1, 17, 0, 1.0, None, None) == -3
+    assert lib.ocf_corr_fwd(one, one, one, 1, 1, 2, 2, 4, 5, 1.0, None, None) == -2  # out_bstride too small
+    assert lib.ocf_corr_bwd(one, None, one, one, None, None, 1, 1, 1, 1, 4, 0, 1.0, None) == -1
+    assert lib.ocf_warp_fwd(one, one, None, one, 1, 1, 1, 1, 8, 1.0, None) == -3
+    assert lib.ocf_warp_bwd(one, one, one, None, None, None, None, 1, 1, 1, 1, 0, 1.0, None) == -1
+    assert lib.ocf_range_map(one, None, None, 1, 1, 1, None) == -1
+    assert lib.ocf_smooth_fwd(one, one, one, 1, 3, 2, 4, 4, 3, 100.0, 0.001, None) == -3
+    assert lib.ocf_pair_loss(one, one, one, None, 4, 9, None) == -3
+    assert lib.ocf_host_corr_fwd(None, None, None, 1, 1, 1, 1, 4) == -1
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from ocflow_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libocflow_b200.so")
+    with pytest.raises(RuntimeError, match="no fallback"):
+        _lib.load()
