@@ -246,7 +246,7 @@ class _Photometric(torch.autograd.Function):
         if occ is not None:
             den = sums[1] * 3 + 1e-16           # the literal 3 of models/model.py:43
         else:
-            den = torch.full((), float(B * C * H * W), device=pred.device, dtype=torch.float64)
+            den = sums[1] * 0 + float(B * C * H * W)   # torch.mean; built from a device scalar (graph-capture safe)
         loss = (sums[0] / den).to(torch.float32)
         ctx.alpha, ctx.has_occ = float(alpha), occ is not None
         if occ is not None:
@@ -303,8 +303,8 @@ class _Smooth(torch.autograd.Function):
         ny = float(B * Cf * (H - order) * W)
         ctx.cfg = (order, float(alpha_edge), float(alpha_rho), nx, ny)
         ctx.save_for_backward(img, flow)
-        scale = torch.tensor([0.5 / nx, 0.5 / ny], device=img.device, dtype=torch.float64)
-        return (sums * scale).sum().to(torch.float32)
+        # python-scalar arithmetic only: no host->device tensor creation, so the op stays CUDA-graph capturable
+        return (sums[0] * (0.5 / nx) + sums[1] * (0.5 / ny)).to(torch.float32)
 
     @staticmethod
     def backward(ctx, g):
@@ -312,7 +312,7 @@ class _Smooth(torch.autograd.Function):
         order, ae, ar, nx, ny = ctx.cfg
         B, Ci, H, W = img.shape
         Cf = flow.shape[1]
-        coef = (g.reshape(1) * torch.tensor([0.5 / nx, 0.5 / ny], device=img.device, dtype=torch.float32)).contiguous()
+        coef = torch.stack((g * (0.5 / nx), g * (0.5 / ny))).to(torch.float32).contiguous()
         need_img, need_flow = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         d_img = torch.empty_like(img) if need_img else None
         d_flow = torch.empty_like(flow) if need_flow else None

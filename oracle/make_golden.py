@@ -22,6 +22,7 @@ from oracle import ref_loader  # noqa: E402
 from oracle import ocflow_oracle as O  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
+FLOW_GAIN = 0.1  # see ocflow_oracle.deterministic_state_dict: keeps the model-level fixture well conditioned
 
 
 def _grads(fn, inputs, seed):
@@ -122,7 +123,7 @@ def op_case(R, name, B, C, H, W, seed, flow_scale, d_list=(4,), integer_flow=Fal
 def net_case(R, B, H, W, seed):
     net = R.cost_volume_flow_net.FlowNetCV()
     shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
-    sd = O.deterministic_state_dict(shapes, seed=seed)
+    sd = O.deterministic_state_dict(shapes, seed=seed, flow_gain=FLOW_GAIN)
     stage = R.model.FlowStageModel({"model": "pwc", "occ_aware": True, "learning_rate": 1e-5,
                                     "photo_weight": 4.0, "smooth1_weight": 0.5, "smooth2_weight": 0.0})
     stage.flow_pred.load_state_dict(sd)
@@ -140,7 +141,7 @@ def net_case(R, B, H, W, seed):
     named = dict(stage.flow_pred.named_parameters())
     grads = {k: named[k].grad.detach().clone() for k in keep}
     gnorm = {k: float(p.grad.norm()) for k, p in named.items() if p.grad is not None}
-    return dict(shapes=shapes, seed=seed, imgs=imgs, flow_gt=flow_gt, occ_gt=occ_gt, ref_flow1=flow1, ref_flow_l2=flow_l2,
+    return dict(shapes=shapes, seed=seed, flow_gain=FLOW_GAIN, imgs=imgs, flow_gt=flow_gt, occ_gt=occ_gt, ref_flow1=flow1, ref_flow_l2=flow_l2,
                 ref_losses=[x.detach() for x in losses], ref_total=loss.detach(), ref_grads=grads, ref_grad_norms=gnorm)
 
 

@@ -364,9 +364,15 @@ def total_loss(losses, photo_weight=4.0, smooth1_weight=0.5, smooth2_weight=0.0)
     return photo_weight * losses[0] + smooth1_weight * losses[1] + smooth2_weight * losses[2]
 
 
-def deterministic_state_dict(shapes, seed=0, dtype=torch.float32):
+def deterministic_state_dict(shapes, seed=0, dtype=torch.float32, flow_gain=1.0):
     """Name-keyed deterministic weights (independent of module construction order) used by the golden
-    fixtures and the GPU parity tests: fan-in-scaled normal weights, small normal biases."""
+    fixtures and the GPU parity tests: fan-in-scaled normal weights, small normal biases.
+
+    flow_gain scales the flow-predicting layers (predict_flow*, dc_conv7).  With gain 1 random weights
+    give ~50 px flows on a 64 px image; the step's gradient is then discontinuous enough (bilinear cell
+    changes, frame exits) that a 1e-6 relative weight perturbation moves parameter gradients by 1e-2
+    in the reference itself -- no implementation can be compared at 1e-3 there.  The model-level
+    fixtures use a small gain so the comparison is well conditioned."""
     sd = {}
     for i, (name, shape) in enumerate(sorted(shapes.items())):
         g = torch.Generator().manual_seed(seed * 100003 + i)
@@ -377,4 +383,6 @@ def deterministic_state_dict(shapes, seed=0, dtype=torch.float32):
             sd[name] = (torch.randn(shape, generator=g, dtype=torch.float64) * (1.0 / math.sqrt(fan))).to(dtype)
         else:
             sd[name] = (torch.randn(shape, generator=g, dtype=torch.float64) * 0.05).to(dtype)
+        if flow_gain != 1.0 and (name.startswith("predict_flow") or name.startswith("dc_conv7")):
+            sd[name] = sd[name] * flow_gain
     return sd
