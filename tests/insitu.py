@@ -51,17 +51,20 @@ def recording():
         out = orig["occ_photo_fused"](img1, img2, flow, rmap, flow_gt, occ_gt, alpha)
 
         def orc(f):
-            i1, i2 = img1.detach().double().cpu(), img2.detach().double().cpu()
-            occ = O.occlusion_from_range_map(rmap.double().cpu()) if rmap is not None else torch.zeros_like(i1[:, :1])
+            dt = f.dtype
+            i1, i2 = img1.detach().to(dt).cpu(), img2.detach().to(dt).cpu()
+            occ = O.occlusion_from_range_map(rmap.to(dt).cpu()) if rmap is not None else torch.zeros_like(i1[:, :1])
             w = O.warp(i2, f, True)
             res = [O.photometric_error(w, i1, occ), O.photometric_error(w, i1, 1.0 - occ)]
             if flow_gt is not None:
-                res.append(((f - flow_gt.double().cpu()) ** 2).mean())
+                res.append(((f - flow_gt.to(dt).cpu()) ** 2).mean())
             if occ_gt is not None:
-                res.append(O.binary_cross_entropy(occ_gt.double().cpu(), occ).mean())
+                res.append(O.binary_cross_entropy(occ_gt.to(dt).cpu(), occ).mean())
             return res
         outs = [out[0], out[1]] + ([out[2]] if flow_gt is not None else []) + ([out[3]] if occ_gt is not None else [])
-        calls.append(("occ_photo_fused", [flow], outs, orc))
+        # fp32 oracle here: the fp32 REFERENCE's d/dflow is itself 2e-4..5e-4 away from fp64 (the normalise /
+        # un-normalise round trip of the sampling grid costs ~2e-6 px), so fp64 would test the reference, not the kernel
+        calls.append(("occ_photo_fused", [flow], outs, orc, torch.float32))
         return out
 
     def sm(img, flow, order, alpha=100.0, alpha_rho=0.001):
@@ -93,7 +96,8 @@ def check(calls, loss, report=None):
     """Backpropagate `loss`, then compare every recorded call with the fp64 oracle.  Returns a list of
     (index, name, shape, [out errors], [grad errors]) -- errors are max|d|/max|ref|."""
     gin, gout = {}, {}
-    for ci, (name, ins, outs, _) in enumerate(calls):
+    for ci, call in enumerate(calls):
+        name, ins, outs = call[0], call[1], call[2]
         for j, t in enumerate(ins):
             if t.requires_grad:
                 t.register_hook(lambda g, k=(ci, j): gin.__setitem__(k, g.detach().clone()))
@@ -102,14 +106,16 @@ def check(calls, loss, report=None):
                 t.register_hook(lambda g, k=(ci, j): gout.__setitem__(k, g.detach().clone()))
     loss.backward()
     rows = []
-    for ci, (name, ins, outs, orc) in enumerate(calls):
-        leaves = [t.detach().double().cpu().requires_grad_(t.requires_grad) for t in ins]
+    for ci, call in enumerate(calls):
+        name, ins, outs, orc = call[:4]
+        dtype = call[4] if len(call) > 4 else torch.float64
+        leaves = [t.detach().to(dtype).cpu().requires_grad_(t.requires_grad) for t in ins]
         ro = orc(*leaves)
         oerr = [rel_max(o, r) for o, r in zip(outs, ro)]
         gerr = []
         cots = [(j, gout[(ci, j)]) for j in range(len(outs)) if (ci, j) in gout]
         if cots and any(l.requires_grad for l in leaves):
-            tot = sum((ro[j] * g.double().cpu()).sum() for j, g in cots)
+            tot = sum((ro[j] * g.to(dtype).cpu()).sum() for j, g in cots)
             gr = torch.autograd.grad(tot, [l for l in leaves if l.requires_grad], allow_unused=True)
             it = iter(gr)
             for j, l in enumerate(leaves):
