@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-roofline", action="store_true")
+    ap.add_argument("--kernels-only", action="store_true", help="only time the hot-path kernels alone (developer aid)")
+    ap.add_argument("--levels", default="", help="kernels-only: comma list of C:h:w overriding the pyramid levels (e.g. 16:188:621)")
     return ap.parse_args()
 
 
@@ -182,12 +184,20 @@ def kernel_table(args, torch):
     def P(t):
         return ctypes.c_void_p(t.data_ptr())
 
-    for lvl, C in levels.items():
-        h, w = H >> lvl, W >> lvl
+    def smooth_flow(b, h, w, scale):
+        # what the kernels see in the real step: a coarse flow field up-sampled x4 (cost_volume_flow_net.py:182,245),
+        # i.e. spatially coherent displacements -- not per-pixel white noise
+        import torch.nn.functional as F
+        coarse = torch.randn(b, 2, max(h // 4, 2), max(w // 4, 2), device=dev, generator=g) * scale
+        return F.interpolate(coarse, size=(h, w), mode="bilinear", align_corners=True).contiguous()
+
+    custom = [tuple(int(v) for v in item.split(":")) for item in getattr(args, "levels", "").split(",") if item]
+    level_list = [(lvl, C, H >> lvl, W >> lvl) for lvl, C in levels.items()] if not custom else [(i + 1, c, h, w) for i, (c, h, w) in enumerate(custom)]
+    for lvl, C, h, w in level_list:
         n = B * h * w
         f1 = torch.randn(B, C, h, w, device=dev, generator=g)
         f2 = torch.randn(B, C, h, w, device=dev, generator=g)
-        fl = torch.randn(B, 2, h, w, device=dev, generator=g) * 2
+        fl = smooth_flow(B, h, w, 2.0)
         out = torch.empty(B, 81, h, w, device=dev)
         gout = torch.randn(B, 81, h, w, device=dev, generator=g)
         d1, d2 = torch.empty_like(f1), torch.empty_like(f2)
@@ -197,7 +207,7 @@ def kernel_table(args, torch):
             "ocf_corr_fwd", P(f1), P(f2), P(out), B, C, h, w, 4, 0, 0.1, None, st), 4 * n * (2 * C + 81), 2)
         table["corr_bwd_L%d" % lvl] = (lambda gout=gout, out=out, f1=f1, f2=f2, d1=d1, d2=d2, C=C, h=h, w=w: _lib.call(
             "ocf_corr_bwd", P(gout), P(out), P(f1), P(f2), P(d1), P(d2), B, C, h, w, 4, 0, 0.1, st), 4 * n * (81 + 4 * C), 1)
-        if lvl < 6:
+        if lvl < 6 or custom:
             table["warp_fwd_L%d" % lvl] = (lambda f2=f2, fl=fl, wout=wout, C=C, h=h, w=w: _lib.call(
                 "ocf_warp_fwd", P(f2), P(fl), None, P(wout), B, C, h, w, 0, 1.25, st), 4 * n * (2 * C + 2), 2)
             table["warp_bwd_L%d" % lvl] = (lambda f2=f2, fl=fl, wout=wout, d2=d2, dfl=dfl, C=C, h=h, w=w: _lib.call(
@@ -206,7 +216,7 @@ def kernel_table(args, torch):
     n = B * H * W
     i1 = torch.rand(B, 3, H, W, device=dev, generator=g) * 2 - 1
     i2 = torch.rand(B, 3, H, W, device=dev, generator=g) * 2 - 1
-    fw = torch.randn(B, 2, H, W, device=dev, generator=g) * 5
+    fw = smooth_flow(B, H, W, 5.0)
     fg = torch.randn(B, 2, H, W, device=dev, generator=g) * 5
     og = (torch.rand(B, 1, H, W, device=dev, generator=g) < 0.3).float()
     rm = torch.empty(B, 1, H, W, device=dev)
@@ -218,9 +228,19 @@ def kernel_table(args, torch):
     return table
 
 
-def time_kernels(args, torch):
+def time_kernels(args, torch, with_copy_ref=False):
     table = kernel_table(args, torch)
     flush = torch.empty(1024 * 1024 * 1024 // 4, device="cuda")  # 1 GiB >> 126 MB L2; its memset also keeps the GPU busy while the timed launch is enqueued
+    if with_copy_ref:
+        # the practical streaming ceiling AT THIS SIZE: a plain device copy moving the same number of bytes, same harness
+        refs = {}
+        for name, (fn, nbytes, per_step) in list(table.items()):
+            n = max(nbytes // 8, 1)
+            if n not in refs:
+                a, b = torch.empty(n, device="cuda"), torch.empty(n, device="cuda")
+                refs[n] = (a, b)
+            a, b = refs[n]
+            table["copy_same_bytes:" + name] = (lambda a=a, b=b: b.copy_(a), nbytes, 0)
     res = {}
     for name, (fn, nbytes, per_step) in table.items():
         for _ in range(3):
@@ -261,6 +281,16 @@ def main():
     from ocflow_b200.train import TrainStep, build_model, synthetic_batch
 
     _lib.load()
+    if args.kernels_only:
+        peak, _ = measured_peaks()
+        kt = time_kernels(args, torch, with_copy_ref=True)
+        for k, v in kt.items():
+            if k.startswith("copy_same_bytes:"):
+                continue
+            ref = kt.get("copy_same_bytes:" + k)
+            print("%-18s %9.2f us  %8.1f GB/s  %.3f of measured HBM peak   (torch copy of the same bytes: %7.2f us -> %.2f of that)" % (
+                k, v["us"], v["gbs"], v["gbs"] / peak, ref["us"], ref["us"] / v["us"]))
+        return
     torch.backends.cudnn.benchmark = True
     torch.backends.cudnn.allow_tf32 = bool(args.tf32)
     torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)

@@ -3,19 +3,36 @@
 // Replaces compute_cost_volume (reference models/networks/correlation_layer.py:7-40): 81 x
 // (slice, mul, mean) + cat => one launch.  See DESIGN.md "corr" for the tiling rationale.
 //
-//   forward : a CTA owns a TH x TW pixel tile of one batch item.  Per channel chunk it stages the f1
-//             tile and the f2 tile + halo in shared memory (row strides == 4 mod 8 floats so that the
-//             128-bit window loads of a quarter-warp hit 8 distinct bank groups).  Warp w of the CTA
-//             owns the vertical displacement dy = w - d; a thread owns PX consecutive pixels of one
-//             row and all 2d+1 horizontal displacements: (2d+1)*PX register accumulators,
+//   staging : when rows are 16-byte aligned (W % 4 == 0: FlyingChairs / any multiple-of-64 crop) the f1 tile and the
+//             f2 tile + halo of a channel chunk are ONE TMA box each (cp.async.bulk.tensor.4d over the NCHW tensor,
+//             out-of-image and past-the-last-channel elements zero-filled by the TMA unit), issued by a single
+//             producer thread into a STAGES-deep ring guarded by full/empty mbarriers -- the 9 compute warps never
+//             execute a staging instruction or a __syncthreads in the main loop.  Ragged widths (KITTI/Sintel
+//             pyramids: 621, 311, 109 ... where TMA's 16-byte global strides are illegal) use a cp.async ring with
+//             element-wise zero-fill instead.
+//   forward : a CTA owns a TH x TW pixel tile of one batch item (and, for the small pyramid levels, one
+//             slice of the channels).  Shared-memory row strides are == 4 mod 8 floats so the 128-bit window
+//             loads of a quarter-warp hit 8 distinct bank groups.  Warp w owns the vertical displacement dy = w - d; a thread owns PX consecutive pixels
+//             of one row and all 2d+1 horizontal displacements: (2d+1)*PX register accumulators,
 //             (PX + PX+2d)/4 LDS.128 per (2d+1)*PX FMAs.
+//             Small levels (few tiles, many channels) split the channels over a thread-block CLUSTER; the
+//             partial cost volumes are reduced through distributed shared memory (deterministic, no atomics,
+//             the 1/C scale and the LeakyReLU stay fused).
 //   backward: d f1 and d f2 are both written as gathers (deterministic, no atomics):
 //               d f1[c,p] = 1/C sum_delta g[delta, p]        * f2[c, p+delta]
 //               d f2[c,q] = 1/C sum_delta g[-delta, q+delta] * f1[c, q+delta]
 //             i.e. the same "window of the other feature times 81 per-pixel coefficients"; only the
 //             way the coefficients are fetched differs.  A thread keeps its (2d+1)*PX coefficients
-//             in registers for the whole kernel, the 2d+1 dy-warps reduce through shared memory.
+//             in registers for the whole kernel, the 2d+1 dy-warps reduce through shared memory.  Channels
+//             are independent here, so small levels simply split them over more CTAs.
+#include <cooperative_groups.h>
+#include <cuda.h>  // CUtensorMap types only; the driver entry point is fetched at run time (no libcuda link dependency)
+
+#include <string.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -24,9 +41,9 @@ constexpr int pad4mod8(int n) {
   return (r % 8 == 4) ? r : r + 4;
 }
 
-template <int D_, int PX_, int TXT_, int TH_, int CC_>
+template <int D_, int PX_, int TXT_, int TH_, int CC_, int STAGES_>
 struct CorrTile {
-  static constexpr int D = D_, PX = PX_, TXT = TXT_, TH = TH_, CC = CC_;
+  static constexpr int D = D_, PX = PX_, TXT = TXT_, TH = TH_, CC = CC_, STAGES = STAGES_;
   static constexpr int ND = 2 * D + 1;
   static constexpr int TW = PX * TXT;
   static constexpr int F2W = TW + 2 * D;
@@ -36,71 +53,140 @@ struct CorrTile {
   static constexpr int LANES = TXT * TH;  // pixel-threads per dy (one warp when == 32)
   static constexpr int THREADS = LANES * ND;
   static constexpr int WIN = PX + 2 * D;  // f2 window per thread
+  static constexpr int F1_STAGE = CC * TH * S1;    // floats per stage
+  static constexpr int F2_STAGE = CC * F2H * S2;
   static_assert(PX % 4 == 0 && (2 * D) % 4 == 0, "128-bit window loads need PX and 2D multiples of 4");
   static_assert(LANES == 32, "one warp per vertical displacement");
 };
 
-// ---- tile staging -------------------------------------------------------------------------------
-// Copies a [CC][ROWS][COLS] box of a NCHW tensor (origin (yb, xb), may be negative / past the edge)
-// into shared memory with row stride S, zero-filling everything outside the image or past channel C.
-// VEC: rows are 16-byte aligned in global memory (W % 4 == 0, xb % 4 == 0, base aligned).
+// ---- cp.async helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;  // src-size 0 => the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---- TMA + mbarrier helpers ---------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = smem_u32(bar);
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// one 4-D box {x, y, c, b} of an NCHW fp32 tensor -> dense [c][y][x] box in shared memory; signals `bar` with the byte count
+__device__ __forceinline__ void tma_load_4d(float* smem_dst, const CUtensorMap* map, unsigned long long* bar, int x, int y, int c,
+                                            int b) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(c), "r"(b)
+      : "memory");
+}
+template <int THREADS>
+__device__ __forceinline__ void consumer_bar_sync() {  // named barrier 1: the compute warps only (the producer warp is not part)
+  asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+}
+
+// Asynchronously copies a [CC][ROWS][COLS] box of one batch item of a NCHW tensor (origin (yb, xb), may be negative
+// or past the edge; channels [c0, c0+CC) clipped to c_end) into shared memory with row stride S; everything outside
+// is zero-filled by the copy engine.  VEC: rows are 16-byte aligned in global memory (W % 4 == 0, xb % 4 == 0).
 template <int CC, int ROWS, int COLS, int S, int THREADS, bool VEC>
-__device__ __forceinline__ void stage_box(float* __restrict__ dst, const float* __restrict__ src_b, int c0, int C,
-                                          int H, int W, int yb, int xb, float nmean, float ninv, bool do_norm) {
+__device__ __forceinline__ void stage_box_async(float* __restrict__ dst, const float* __restrict__ src_b, int c0, int c_end,
+                                                int H, int W, int yb, int xb) {
   if (VEC) {
     constexpr int C4 = COLS / 4;
     constexpr int ITEMS = CC * ROWS * C4;
+#pragma unroll 4
     for (int i = threadIdx.x; i < ITEMS; i += THREADS) {
       const int row = i / C4, q = i - row * C4;
       const int c = row / ROWS, r = row - c * ROWS;
       const int gy = yb + r, gx = xb + q * 4, gc = c0 + c;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gc < C && gy >= 0 && gy < H && gx >= 0 && gx < W) {
-        v = __ldg(reinterpret_cast<const float4*>(src_b + ((size_t)gc * H + gy) * W + gx));
-        if (do_norm) {
-          v.x = (v.x - nmean) * ninv; v.y = (v.y - nmean) * ninv;
-          v.z = (v.z - nmean) * ninv; v.w = (v.w - nmean) * ninv;
-        }
-      }
-      *reinterpret_cast<float4*>(dst + (c * ROWS + r) * S + q * 4) = v;
+      const bool ok = gc < c_end && gy >= 0 && gy < H && gx >= 0 && gx < W;
+      const float* src = ok ? src_b + ((size_t)gc * H + gy) * W + gx : src_b;
+      cp_async16(dst + (c * ROWS + r) * S + q * 4, src, ok);
     }
   } else {
     constexpr int ITEMS = CC * ROWS * COLS;
+#pragma unroll 4
     for (int i = threadIdx.x; i < ITEMS; i += THREADS) {
       const int row = i / COLS, x = i - row * COLS;
       const int c = row / ROWS, r = row - c * ROWS;
       const int gy = yb + r, gx = xb + x, gc = c0 + c;
-      float v = 0.f;
-      if (gc < C && gy >= 0 && gy < H && gx >= 0 && gx < W) {
-        v = __ldg(src_b + ((size_t)gc * H + gy) * W + gx);
-        if (do_norm) v = (v - nmean) * ninv;
-      }
-      dst[(c * ROWS + r) * S + x] = v;
+      const bool ok = gc < c_end && gy >= 0 && gy < H && gx >= 0 && gx < W;
+      const float* src = ok ? src_b + ((size_t)gc * H + gy) * W + gx : src_b;
+      cp_async4(dst + (c * ROWS + r) * S + x, src, ok);
     }
   }
 }
 
+// ---- staging modes ------------------------------------------------------------------------------
+constexpr int STG_ASYNC4 = 0;   // cp.async, 4-byte elements (ragged widths)
+constexpr int STG_ASYNC16 = 1;  // cp.async, 16-byte elements
+constexpr int STG_TMA = 2;      // TMA boxes + mbarrier ring, dedicated producer warp
+
+template <class T, int STG>
+struct Threads {
+  static constexpr int value = T::THREADS + (STG == STG_TMA ? 32 : 0);
+};
+
+struct ChunkRange {
+  int begin, count;
+};
+// channel chunks [begin, begin+count) of this CTA: whole chunks only, so a TMA box never straddles two slices
+__device__ __forceinline__ ChunkRange chunk_range(int C, int CC, int ksplit, int ks) {
+  const int total = (C + CC - 1) / CC;
+  const int per = (total + ksplit - 1) / ksplit;
+  ChunkRange r;
+  r.begin = ks * per;
+  r.count = max(0, min(total, r.begin + per) - r.begin);
+  return r;
+}
+
 // ---- forward ------------------------------------------------------------------------------------
-template <class T, bool VEC>
-__global__ void __launch_bounds__(T::THREADS, 2)
-corr_fwd_tiled(const float* __restrict__ f1, const float* __restrict__ f2, float* __restrict__ out, int C, int H, int W,
-               long long out_bstride, float inv_c, float slope, const float* __restrict__ norm) {
-  constexpr int D = T::D, PX = T::PX, ND = T::ND, TH = T::TH, TW = T::TW, CC = T::CC;
+// grid (tiles_x, tiles_y, B * ksplit); when ksplit > 1 the launch carries cluster dims (1, 1, ksplit).
+template <class T, int STG>
+__global__ void __launch_bounds__(Threads<T, STG>::value, 2)
+corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2, const float* __restrict__ f1,
+               const float* __restrict__ f2, float* __restrict__ out, int C, int H, int W, long long out_bstride, float inv_c,
+               float slope, int ksplit) {
+  constexpr int D = T::D, PX = T::PX, ND = T::ND, TH = T::TH, TW = T::TW, CC = T::CC, STAGES = T::STAGES;
   constexpr int S1 = T::S1, S2 = T::S2, F2H = T::F2H, F2W = T::F2W, WIN = T::WIN;
-  extern __shared__ __align__(16) float smem[];
-  float* f1s = smem;                 // [CC][TH][S1]
-  float* f2s = smem + CC * TH * S1;  // [CC][F2H][S2]
+  constexpr int STAGE = T::F1_STAGE + T::F2_STAGE;
+  constexpr bool TMA = STG == STG_TMA;
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES];
 
   const int tid = threadIdx.x;
   const int lane = tid % T::LANES;
   const int tx = lane % T::TXT, ty = lane / T::TXT;
-  const int dyi = tid / T::LANES;
-  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
-  const float* f1b = f1 + (size_t)b * C * H * W;
-  const float* f2b = f2 + (size_t)b * C * H * W;
-  float nmean = 0.f, ninv = 1.f;
-  const bool do_norm = norm != nullptr;
-  if (do_norm) { nmean = __ldg(norm); ninv = __ldg(norm + 1); }
+  const int dyi = tid / T::LANES;  // == ND for the TMA producer warp
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  const int b = blockIdx.z / ksplit, ks = blockIdx.z - b * ksplit;
+  const ChunkRange cr = chunk_range(C, CC, ksplit, ks);
+  const int nchunks = cr.count;
 
   float acc[ND][PX];
 #pragma unroll
@@ -108,56 +194,154 @@ corr_fwd_tiled(const float* __restrict__ f1, const float* __restrict__ f2, float
 #pragma unroll
     for (int p = 0; p < PX; ++p) acc[i][p] = 0.f;
 
-  for (int c0 = 0; c0 < C; c0 += CC) {
-    __syncthreads();
-    stage_box<CC, TH, TW, S1, T::THREADS, VEC>(f1s, f1b, c0, C, H, W, y0, x0, nmean, ninv, do_norm);
-    stage_box<CC, F2H, F2W, S2, T::THREADS, VEC>(f2s, f2b, c0, C, H, W, y0 - D, x0 - D, nmean, ninv, do_norm);
-    __syncthreads();
-    const float* p1 = f1s + ty * S1 + tx * PX;
-    const float* p2 = f2s + (ty + dyi) * S2 + tx * PX;
+  auto compute = [&](const float* st) {
+    const float* p1 = st + ty * S1 + tx * PX;
+    const float* p2 = st + T::F1_STAGE + (ty + dyi) * S2 + tx * PX;
 #pragma unroll 2
     for (int c = 0; c < CC; ++c) {
       float a[PX], w[WIN];
 #pragma unroll
-      for (int i = 0; i < PX / 4; ++i) {
-        const float4 v = *reinterpret_cast<const float4*>(p1 + c * TH * S1 + 4 * i);
-        a[4 * i] = v.x; a[4 * i + 1] = v.y; a[4 * i + 2] = v.z; a[4 * i + 3] = v.w;
+      for (int q = 0; q < PX / 4; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(p1 + c * TH * S1 + 4 * q);
+        a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
       }
 #pragma unroll
-      for (int i = 0; i < WIN / 4; ++i) {
-        const float4 v = *reinterpret_cast<const float4*>(p2 + c * F2H * S2 + 4 * i);
-        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+      for (int q = 0; q < WIN / 4; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(p2 + c * F2H * S2 + 4 * q);
+        w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
       }
 #pragma unroll
       for (int dx = 0; dx < ND; ++dx)
 #pragma unroll
         for (int p = 0; p < PX; ++p) acc[dx][p] = fmaf(a[p], w[p + dx], acc[dx][p]);
     }
+  };
+
+  if constexpr (TMA) {
+    if (tid == 0) {
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ND); }
+      mbar_fence_init();
+    }
+    __syncthreads();
+    if (dyi == ND) {  // producer warp: one elected lane feeds the ring
+      if (lane == 0) {
+        constexpr unsigned BYTES = sizeof(float) * STAGE;
+        for (int i = 0; i < nchunks; ++i) {
+          const int s = i % STAGES;
+          if (i >= STAGES) mbar_wait(&empty_bar[s], ((i / STAGES) - 1) & 1);
+          float* st = smem + s * STAGE;
+          const int c0 = (cr.begin + i) * CC;
+          mbar_expect_tx(&full_bar[s], BYTES);
+          tma_load_4d(st, &map1, &full_bar[s], x0, y0, c0, b);
+          tma_load_4d(st + T::F1_STAGE, &map2, &full_bar[s], x0 - D, y0 - D, c0, b);
+        }
+      }
+    } else {
+      for (int i = 0; i < nchunks; ++i) {
+        const int s = i % STAGES;
+        mbar_wait(&full_bar[s], (i / STAGES) & 1);
+        compute(smem + s * STAGE);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+      }
+    }
+  } else {
+    const float* f1b = f1 + (size_t)b * C * H * W;
+    const float* f2b = f2 + (size_t)b * C * H * W;
+    auto issue = [&](int i) {
+      float* st = smem + (i % STAGES) * STAGE;
+      const int c0 = (cr.begin + i) * CC;
+      stage_box_async<CC, TH, TW, S1, T::THREADS, STG == STG_ASYNC16>(st, f1b, c0, C, H, W, y0, x0);
+      stage_box_async<CC, F2H, F2W, S2, T::THREADS, STG == STG_ASYNC16>(st + T::F1_STAGE, f2b, c0, C, H, W, y0 - D, x0 - D);
+    };
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+      if (s < nchunks) issue(s);
+      cp_async_commit();
+    }
+    for (int i = 0; i < nchunks; ++i) {
+      cp_async_wait<STAGES - 2>();  // chunk i has landed (for this thread's copies) ...
+      __syncthreads();              // ... and for everybody's; everybody is also done computing chunk i-1
+      if (i + STAGES - 1 < nchunks) issue(i + STAGES - 1);
+      cp_async_commit();
+      compute(smem + (i % STAGES) * STAGE);
+    }
+    cp_async_wait<0>();
   }
 
-  const int y = y0 + ty, xs = x0 + tx * PX;
-  if (y >= H || xs >= W) return;
   const size_t bstride = out_bstride ? (size_t)out_bstride : (size_t)ND * ND * H * W;
-  float* ob = out + (size_t)b * bstride + ((size_t)(dyi * ND) * H + y) * W + xs;
+  constexpr bool VEC = STG != STG_ASYNC4;
+  if (ksplit == 1) {
+    const int y = y0 + ty, xs = x0 + tx * PX;
+    if (dyi >= ND || y >= H || xs >= W) return;
+    float* ob = out + (size_t)b * bstride + ((size_t)(dyi * ND) * H + y) * W + xs;
 #pragma unroll
-  for (int dx = 0; dx < ND; ++dx) {
-    float r[PX];
+    for (int dx = 0; dx < ND; ++dx) {
+      float r[PX];
 #pragma unroll
-    for (int p = 0; p < PX; ++p) {
-      float v = acc[dx][p] * inv_c;
-      r[p] = v > 0.f ? v : v * slope;
+      for (int p = 0; p < PX; ++p) {
+        const float v = acc[dx][p] * inv_c;
+        r[p] = v > 0.f ? v : v * slope;
+      }
+      float* o = ob + (size_t)dx * H * W;
+      if (VEC) {  // W % 4 == 0 and 16B-aligned rows: each float4 is entirely inside or outside
+#pragma unroll
+        for (int q = 0; q < PX / 4; ++q)
+          if (xs + 4 * q < W) *reinterpret_cast<float4*>(o + 4 * q) = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+      } else {
+#pragma unroll
+        for (int p = 0; p < PX; ++p)
+          if (xs + p < W) o[p] = r[p];
+      }
     }
-    float* o = ob + (size_t)dx * H * W;
-    if (VEC) {  // W % 4 == 0 and 16B-aligned rows: each float4 is entirely inside or outside
+    return;
+  }
+
+  // ---- channel-split: reduce the ksplit partial cost volumes of the cluster through DSMEM ----
+  cg::cluster_group cluster = cg::this_cluster();
+  __syncthreads();  // every warp is done reading the staging ring; reuse it as the partial tile [ND*ND][TH][S1]
+  float* part = smem;
+  static_assert(T::STAGES * STAGE >= ND * ND * TH * S1, "staging ring too small to hold the partial cost volume tile");
+  if (dyi < ND) {
 #pragma unroll
-      for (int i = 0; i < PX / 4; ++i)
-        if (xs + 4 * i < W) *reinterpret_cast<float4*>(o + 4 * i) = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
-    } else {
+    for (int dx = 0; dx < ND; ++dx) {
+      float* pp = part + ((dyi * ND + dx) * TH + ty) * S1 + tx * PX;
 #pragma unroll
-      for (int p = 0; p < PX; ++p)
-        if (xs + p < W) o[p] = r[p];
+      for (int q = 0; q < PX / 4; ++q)
+        *reinterpret_cast<float4*>(pp + 4 * q) = make_float4(acc[dx][4 * q], acc[dx][4 * q + 1], acc[dx][4 * q + 2], acc[dx][4 * q + 3]);
     }
   }
+  cluster.sync();
+  // rank r finalises planes k = r, r + ksplit, ...
+  const unsigned rank = cluster.block_rank();
+  constexpr int ROW4 = TW / 4;
+  for (int k = (int)rank; k < ND * ND; k += ksplit) {
+    for (int i = tid; i < TH * ROW4; i += blockDim.x) {
+      const int ry = i / ROW4, x4 = i - ry * ROW4;
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = 0; q < ksplit; ++q) {
+        const float* peer = cluster.map_shared_rank(part, q);
+        const float4 v = *reinterpret_cast<const float4*>(peer + (k * TH + ry) * S1 + x4 * 4);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+      const int y = y0 + ry, x = x0 + x4 * 4;
+      if (y < H && x < W) {
+        float r[4] = {s.x * inv_c, s.y * inv_c, s.z * inv_c, s.w * inv_c};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r[j] = r[j] > 0.f ? r[j] : r[j] * slope;
+        float* o = out + (size_t)b * bstride + ((size_t)k * H + y) * W + x;
+        if (VEC) {
+          *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (x + j < W) o[j] = r[j];
+        }
+      }
+    }
+  }
+  cluster.sync();  // nobody may exit while a peer still reads its shared memory
 }
 
 // Any displacement up to OCF_MAX_DISPLACEMENT: one thread per (pixel, dy), operands through L1/L2.
@@ -199,33 +383,125 @@ corr_fwd_generic(const float* __restrict__ f1, const float* __restrict__ f2, flo
 }
 
 // ---- backward -----------------------------------------------------------------------------------
-// mode 0: dout = d f1, fo = f2 ; mode 1: dout = d f2, fo = f1.  blockIdx.z = b * nmodes + slot.
-template <class T, int CR, bool VEC>
-__global__ void __launch_bounds__(T::THREADS, 2)
-corr_bwd_tiled(const float* __restrict__ g, const float* __restrict__ oact, const float* __restrict__ f1,
-               const float* __restrict__ f2, float* __restrict__ df1, float* __restrict__ df2, int C, int H, int W,
-               long long g_bstride, float inv_c, float slope, int nmodes, int first_mode) {
-  constexpr int D = T::D, PX = T::PX, ND = T::ND, TH = T::TH, TW = T::TW, CC = T::CC;
+// mode 0: dout = d f1, fo = f2 ; mode 1: dout = d f2, fo = f1.
+// blockIdx.z = (b * nmodes + slot) * ksplit + channel slice.
+template <class T, int CR, int STG>
+__global__ void __launch_bounds__(Threads<T, STG>::value, 2)
+corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
+               const __grid_constant__ CUtensorMap mapg, const __grid_constant__ CUtensorMap mapa, const float* __restrict__ g,
+               const float* __restrict__ oact, const float* __restrict__ f1, const float* __restrict__ f2, float* __restrict__ df1,
+               float* __restrict__ df2, int C, int H, int W, long long g_bstride, float inv_c, float slope, int nmodes,
+               int first_mode, int ksplit) {
+  constexpr int D = T::D, PX = T::PX, ND = T::ND, TH = T::TH, TW = T::TW, CC = T::CC, STAGES = T::STAGES;
   constexpr int S1 = T::S1, S2 = T::S2, F2H = T::F2H, F2W = T::F2W, WIN = T::WIN;
+  constexpr bool TMA = STG == STG_TMA;
+  constexpr bool VEC = STG != STG_ASYNC4;
   static_assert(CC % CR == 0, "CC must be a multiple of CR");
-  extern __shared__ __align__(16) float smem[];
-  float* fos = smem;                   // [CC][F2H][S2]
-  float* red = smem + CC * F2H * S2;   // [ND][CR][TH][S1]
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES], g_bar, gdone_bar;
+  float* red = smem + STAGES * T::F2_STAGE;  // [ND][CR][TH][S1]
+  // TMA variant: the 81 coefficient planes of the tile are staged through shared memory first (one {GW, TH, ND} box per
+  // dy-warp, GW == 12 mod 32 floats so the 128-bit reads are conflict-free); the area is then reused by the ring + red.
+  constexpr int GW = T::S2, BOXG = ND * TH * GW;
 
   const int tid = threadIdx.x;
   const int lane = tid % T::LANES;
   const int tx = lane % T::TXT, ty = lane / T::TXT;
-  const int dyi = tid / T::LANES;
+  const int dyi = tid / T::LANES;  // == ND for the TMA producer warp
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-  const int b = blockIdx.z / nmodes;
-  const int mode = first_mode + (blockIdx.z - b * nmodes);
-  const float* fo = (mode == 0 ? f2 : f1) + (size_t)b * C * H * W;
+  const int zz = blockIdx.z / ksplit, ks = blockIdx.z - zz * ksplit;
+  const int b = zz / nmodes;
+  const int mode = first_mode + (zz - b * nmodes);
+  const ChunkRange cr = chunk_range(C, CC, ksplit, ks);
+  const int nchunks = cr.count;
   float* dout = (mode == 0 ? df1 : df2) + (size_t)b * C * H * W;
   const size_t gb = (g_bstride ? (size_t)g_bstride : (size_t)ND * ND * H * W) * b;
 
-  // 81 per-pixel coefficients of this thread's dy row, kept in registers for the whole kernel
-  float G[ND][PX];
-  {
+  float G[ND][PX];  // 81 per-pixel coefficients of this thread's dy row, kept in registers for the whole kernel
+  if constexpr (TMA) {
+    if (tid == 0) {
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ND); }
+      mbar_init(&g_bar, 1);
+      mbar_init(&gdone_bar, ND);
+      mbar_fence_init();
+    }
+    __syncthreads();
+    const bool has_act = oact != nullptr;
+    if (dyi == ND) {
+      if (lane == 0) {
+        // coefficient boxes: mode 0 -> planes dy*ND.. at (y0, x0) ; mode 1 -> planes (2D-dy)*ND.. at (y0+dy-D, x0-D)
+        constexpr unsigned GBYTES = sizeof(float) * ND * BOXG;
+        for (int pass = 0; pass < (has_act ? 2 : 1); ++pass) {
+          if (pass == 1) mbar_wait(&gdone_bar, 0);  // every warp has lifted its coefficients out of the staging area
+          mbar_expect_tx(&g_bar, GBYTES);
+          for (int w = 0; w < ND; ++w) {
+            const int plane0 = mode == 0 ? w * ND : (2 * D - w) * ND;
+            tma_load_4d(smem + w * BOXG, pass == 0 ? &mapg : &mapa, &g_bar, mode == 0 ? x0 : x0 - D, mode == 0 ? y0 : y0 + w - D, plane0, b);
+          }
+        }
+        mbar_wait(&gdone_bar, has_act ? 1 : 0);  // staging area is free: start feeding the feature ring
+        constexpr unsigned BYTES = sizeof(float) * T::F2_STAGE;
+        const CUtensorMap* map = mode == 0 ? &map2 : &map1;  // the OTHER feature
+        for (int i = 0; i < nchunks; ++i) {
+          const int s = i % STAGES;
+          if (i >= STAGES) mbar_wait(&empty_bar[s], ((i / STAGES) - 1) & 1);
+          mbar_expect_tx(&full_bar[s], BYTES);
+          tma_load_4d(smem + s * T::F2_STAGE, map, &full_bar[s], x0 - D, y0 - D, (cr.begin + i) * CC, b);
+        }
+      }
+      return;  // the producer warp takes no part in the compute-warp barriers below
+    }
+    const float* gw = smem + dyi * BOXG + ty * GW + tx * PX;
+    for (int pass = 0; pass < (has_act ? 2 : 1); ++pass) {
+      mbar_wait(&g_bar, pass);
+      if (mode == 0) {
+#pragma unroll
+        for (int dx = 0; dx < ND; ++dx) {
+          float t[PX];
+#pragma unroll
+          for (int q = 0; q < PX / 4; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(gw + dx * TH * GW + 4 * q);
+            t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
+          }
+#pragma unroll
+          for (int p = 0; p < PX; ++p) {
+            if (pass == 0) G[dx][p] = t[p];
+            else if (!(t[p] > 0.f)) G[dx][p] *= slope;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int dx = 0; dx < ND; ++dx) {
+          float t[PX + 4];
+#pragma unroll
+          for (int q = 0; q < PX / 4 + 1; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(gw + (2 * D - dx) * TH * GW + (dx & ~3) + 4 * q);
+            t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
+          }
+#pragma unroll
+          for (int p = 0; p < PX; ++p) {
+            const float v = t[p + (dx & 3)];
+            if (pass == 0) G[dx][p] = v;
+            else if (!(v > 0.f)) G[dx][p] *= slope;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&gdone_bar);
+    }
+  }
+  const float* fo = (mode == 0 ? f2 : f1) + (size_t)b * C * H * W;
+  auto issue = [&](int i) {
+    stage_box_async<CC, F2H, F2W, S2, T::THREADS, STG == STG_ASYNC16>(smem + (i % STAGES) * T::F2_STAGE, fo, (cr.begin + i) * CC, C, H, W,
+                                                                      y0 - D, x0 - D);
+  };
+  if constexpr (!TMA) {
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+      if (s < nchunks) issue(s);
+      cp_async_commit();
+    }
     const int y = y0 + ty, xs = x0 + tx * PX;
 #pragma unroll
     for (int dx = 0; dx < ND; ++dx) {
@@ -247,21 +523,28 @@ corr_bwd_tiled(const float* __restrict__ g, const float* __restrict__ oact, cons
     }
   }
 
-  for (int c0 = 0; c0 < C; c0 += CC) {
-    __syncthreads();
-    stage_box<CC, F2H, F2W, S2, T::THREADS, VEC>(fos, fo, c0, C, H, W, y0 - D, x0 - D, 0.f, 1.f, false);
-    __syncthreads();
-    const float* pw = fos + (ty + dyi) * S2 + tx * PX;
+  for (int i = 0; i < nchunks; ++i) {
+    const int s = i % STAGES;
+    if constexpr (TMA) {
+      mbar_wait(&full_bar[s], (i / STAGES) & 1);
+    } else {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+      if (i + STAGES - 1 < nchunks) issue(i + STAGES - 1);
+      cp_async_commit();
+    }
+    const int c0 = (cr.begin + i) * CC;
+    const float* pw = smem + s * T::F2_STAGE + (ty + dyi) * S2 + tx * PX;
 #pragma unroll 1
     for (int r0 = 0; r0 < CC; r0 += CR) {
       if (c0 + r0 >= C) break;  // uniform across the block
 #pragma unroll
-      for (int cr = 0; cr < CR; ++cr) {
+      for (int c = 0; c < CR; ++c) {
         float w[WIN], part[PX];
 #pragma unroll
-        for (int i = 0; i < WIN / 4; ++i) {
-          const float4 v = *reinterpret_cast<const float4*>(pw + (r0 + cr) * F2H * S2 + 4 * i);
-          w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        for (int q = 0; q < WIN / 4; ++q) {
+          const float4 v = *reinterpret_cast<const float4*>(pw + (r0 + c) * F2H * S2 + 4 * q);
+          w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
         }
 #pragma unroll
         for (int p = 0; p < PX; ++p) part[p] = 0.f;
@@ -269,39 +552,44 @@ corr_bwd_tiled(const float* __restrict__ g, const float* __restrict__ oact, cons
         for (int dx = 0; dx < ND; ++dx)
 #pragma unroll
           for (int p = 0; p < PX; ++p) part[p] = fmaf(G[dx][p], w[p + dx], part[p]);
-        float* rp = red + ((dyi * CR + cr) * TH + ty) * S1 + tx * PX;
+        float* rp = red + ((dyi * CR + c) * TH + ty) * S1 + tx * PX;
 #pragma unroll
-        for (int i = 0; i < PX / 4; ++i)
-          *reinterpret_cast<float4*>(rp + 4 * i) = make_float4(part[4 * i], part[4 * i + 1], part[4 * i + 2], part[4 * i + 3]);
+        for (int q = 0; q < PX / 4; ++q)
+          *reinterpret_cast<float4*>(rp + 4 * q) = make_float4(part[4 * q], part[4 * q + 1], part[4 * q + 2], part[4 * q + 3]);
       }
-      __syncthreads();
+      if constexpr (TMA) consumer_bar_sync<T::THREADS>(); else __syncthreads();
       // cross-dy reduction: CR*TH*TW/4 float4 outputs
       constexpr int OUT4 = CR * TH * TW / 4;
-      for (int i = tid; i < OUT4; i += T::THREADS) {
-        const int x4 = i % (TW / 4), row = i / (TW / 4);  // row = cr*TH + ry
-        const int cr = row / TH, ry = row - cr * TH;
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = tid; j < OUT4; j += T::THREADS) {
+        const int x4 = j % (TW / 4), row = j / (TW / 4);  // row = c*TH + ry
+        const int c = row / TH, ry = row - c * TH;
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < ND; ++k) {
-          const float4 v = *reinterpret_cast<const float4*>(red + ((k * CR + cr) * TH + ry) * S1 + x4 * 4);
-          s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+          const float4 v = *reinterpret_cast<const float4*>(red + ((k * CR + c) * TH + ry) * S1 + x4 * 4);
+          sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
         }
-        const int c = c0 + r0 + cr, y = y0 + ry, x = x0 + x4 * 4;
-        if (c < C && y < H && x < W) {
-          float* o = dout + ((size_t)c * H + y) * W + x;
+        const int ch = c0 + r0 + c, y = y0 + ry, x = x0 + x4 * 4;
+        if (ch < C && y < H && x < W) {
+          float* o = dout + ((size_t)ch * H + y) * W + x;
           if (VEC) {
-            *reinterpret_cast<float4*>(o) = make_float4(s.x * inv_c, s.y * inv_c, s.z * inv_c, s.w * inv_c);
+            *reinterpret_cast<float4*>(o) = make_float4(sum.x * inv_c, sum.y * inv_c, sum.z * inv_c, sum.w * inv_c);
           } else {
-            o[0] = s.x * inv_c;
-            if (x + 1 < W) o[1] = s.y * inv_c;
-            if (x + 2 < W) o[2] = s.z * inv_c;
-            if (x + 3 < W) o[3] = s.w * inv_c;
+            o[0] = sum.x * inv_c;
+            if (x + 1 < W) o[1] = sum.y * inv_c;
+            if (x + 2 < W) o[2] = sum.z * inv_c;
+            if (x + 3 < W) o[3] = sum.w * inv_c;
           }
         }
       }
-      __syncthreads();
+      if constexpr (TMA) consumer_bar_sync<T::THREADS>(); else __syncthreads();
+    }
+    if constexpr (TMA) {
+      // the last consumer barrier above ordered every warp's reads of this stage: one arrival per warp frees it
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
   }
+  if constexpr (!TMA) cp_async_wait<0>();
 }
 
 // generic-displacement backward: one thread per (b, c, y, x) element of d f1 / d f2.
@@ -344,7 +632,7 @@ corr_bwd_generic(const float* __restrict__ g, const float* __restrict__ oact, co
   if (df2 != nullptr) df2[fb + pix] = a2 * inv_c;
 }
 
-using Tile4 = CorrTile<4, 8, 4, 8, 16>;
+using Tile4 = CorrTile<4, 8, 4, 8, 8, 3>;
 constexpr int BWD_CR = 4;
 
 template <class K>
@@ -356,6 +644,61 @@ int set_smem(K kernel, size_t bytes) {
   return 0;
 }
 
+// channel split: enough CTAs to cover the 148 SMs twice, at least `min_ch` channels per CTA, power of two <= 8
+int pick_ksplit(long long tiles, int C, int min_ch) {
+  int ks = 1;
+  while (ks < 8 && tiles * ks < 2LL * OCF_SM_COUNT && C / (ks * 2) >= min_ch) ks *= 2;
+  return ks;
+}
+
+template <class K, class... Args>
+int launch_kernel(K kernel, dim3 grid, int threads, size_t smem, cudaStream_t s, int cluster_z, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = cluster_z;
+  cfg.attrs = attr;
+  cfg.numAttrs = cluster_z > 1 ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (the .so must load on a machine without libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// NCHW fp32 tensor [B, C, H, W] -> 4-D tensor map with a {bw, bh, cc, 1} box; out-of-bounds elements read as zero
+bool make_map(CUtensorMap* map, const float* base, int B, int C, int H, int W, int bw, int bh, int cc, long long bstride = 0) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)(bstride ? bstride : (long long)W * H * C) * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)cc, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace
 
 extern "C" int ocf_corr_fwd(const float* f1, const float* f2, float* out, int B, int C, int H, int W, int d,
@@ -365,20 +708,28 @@ extern "C" int ocf_corr_fwd(const float* f1, const float* f2, float* out, int B,
   OCF_REQUIRE(d >= 0 && d <= OCF_MAX_DISPLACEMENT, OCF_EUNSUPPORTED);
   const long long nd = 2 * d + 1;
   OCF_REQUIRE(out_bstride == 0 || out_bstride >= nd * nd * H * W, OCF_ESHAPE);
-  OCF_REQUIRE(B <= 65535, OCF_EUNSUPPORTED);
+  OCF_REQUIRE(B <= 8191, OCF_EUNSUPPORTED);
   cudaStream_t s = ocf_cast_stream(stream);
   const float inv_c = 1.0f / (float)C;
-  if (d == 4) {
+  if (d == 4 && norm == nullptr) {
     using T = Tile4;
-    const size_t smem = sizeof(float) * T::CC * (T::TH * T::S1 + T::F2H * T::S2);
-    dim3 grid((W + T::TW - 1) / T::TW, (H + T::TH - 1) / T::TH, B);
+    const size_t smem = sizeof(float) * T::STAGES * (T::F1_STAGE + T::F2_STAGE);
+    const int gx = (W + T::TW - 1) / T::TW, gy = (H + T::TH - 1) / T::TH;
+    const int ks = pick_ksplit((long long)gx * gy * B, C, 2 * T::CC);
+    dim3 grid(gx, gy, B * ks);
     const bool vec = (W % 4 == 0) && ocf_aligned16(f1) && ocf_aligned16(f2) && ocf_aligned16(out) && (out_bstride % 4 == 0);
-    if (vec) {
-      if (int e = set_smem(corr_fwd_tiled<T, true>, smem)) return e;
-      corr_fwd_tiled<T, true><<<grid, T::THREADS, smem, s>>>(f1, f2, out, C, H, W, out_bstride, inv_c, leaky_slope, norm);
+    CUtensorMap m1, m2;
+    memset(&m1, 0, sizeof(m1));
+    memset(&m2, 0, sizeof(m2));
+    const bool tma = vec && make_map(&m1, f1, B, C, H, W, T::S1, T::TH, T::CC) && make_map(&m2, f2, B, C, H, W, T::S2, T::F2H, T::CC);
+    if (tma) {
+      auto kernel = corr_fwd_tiled<T, STG_TMA>;
+      if (int e = set_smem(kernel, smem)) return e;
+      if (int e = launch_kernel(kernel, grid, T::THREADS + 32, smem, s, ks, m1, m2, f1, f2, out, C, H, W, out_bstride, inv_c, leaky_slope, ks)) return e;
     } else {
-      if (int e = set_smem(corr_fwd_tiled<T, false>, smem)) return e;
-      corr_fwd_tiled<T, false><<<grid, T::THREADS, smem, s>>>(f1, f2, out, C, H, W, out_bstride, inv_c, leaky_slope, norm);
+      auto kernel = vec ? corr_fwd_tiled<T, STG_ASYNC16> : corr_fwd_tiled<T, STG_ASYNC4>;
+      if (int e = set_smem(kernel, smem)) return e;
+      if (int e = launch_kernel(kernel, grid, T::THREADS, smem, s, ks, m1, m2, f1, f2, out, C, H, W, out_bstride, inv_c, leaky_slope, ks)) return e;
     }
   } else {
     dim3 grid((H * W + 127) / 128, (unsigned)nd, B);
@@ -396,25 +747,41 @@ extern "C" int ocf_corr_bwd(const float* grad_out, const float* out_act, const f
   OCF_REQUIRE(d >= 0 && d <= OCF_MAX_DISPLACEMENT, OCF_EUNSUPPORTED);
   const long long nd = 2 * d + 1;
   OCF_REQUIRE(g_bstride == 0 || g_bstride >= nd * nd * H * W, OCF_ESHAPE);
-  OCF_REQUIRE(B <= 32767 && C <= 65535, OCF_EUNSUPPORTED);
+  OCF_REQUIRE(B <= 4095 && C <= 65535, OCF_EUNSUPPORTED);
   cudaStream_t s = ocf_cast_stream(stream);
   const float inv_c = 1.0f / (float)C;
   if (d == 4) {
     using T = Tile4;
-    const size_t smem = sizeof(float) * (T::CC * T::F2H * T::S2 + T::ND * BWD_CR * T::TH * T::S1);
+    size_t smem = sizeof(float) * (T::STAGES * T::F2_STAGE + T::ND * BWD_CR * T::TH * T::S1);
     const int nmodes = (df1 != nullptr && df2 != nullptr) ? 2 : 1;
     const int first = df1 != nullptr ? 0 : 1;
-    dim3 grid((W + T::TW - 1) / T::TW, (H + T::TH - 1) / T::TH, B * nmodes);
+    const int gx = (W + T::TW - 1) / T::TW, gy = (H + T::TH - 1) / T::TH;
+    const int ks = pick_ksplit((long long)gx * gy * B * nmodes, C, 2 * T::CC);
+    dim3 grid(gx, gy, B * nmodes * ks);
     const bool vec = (W % 4 == 0) && ocf_aligned16(f1) && ocf_aligned16(f2) && (df1 == nullptr || ocf_aligned16(df1)) &&
                      (df2 == nullptr || ocf_aligned16(df2));
-    if (vec) {
-      if (int e = set_smem(corr_bwd_tiled<T, BWD_CR, true>, smem)) return e;
-      corr_bwd_tiled<T, BWD_CR, true><<<grid, T::THREADS, smem, s>>>(grad_out, out_act, f1, f2, df1, df2, C, H, W, g_bstride,
-                                                                    inv_c, leaky_slope, nmodes, first);
+    CUtensorMap m1, m2, mg, ma;
+    memset(&m1, 0, sizeof(m1));
+    memset(&m2, 0, sizeof(m2));
+    memset(&mg, 0, sizeof(mg));
+    memset(&ma, 0, sizeof(ma));
+    const long long gbs = g_bstride ? g_bstride : nd * nd * H * W;
+    bool tma = vec && ocf_aligned16(grad_out) && (out_act == nullptr || ocf_aligned16(out_act)) && (gbs % 4 == 0);
+    tma = tma && make_map(&m1, f1, B, C, H, W, T::S2, T::F2H, T::CC) && make_map(&m2, f2, B, C, H, W, T::S2, T::F2H, T::CC) &&
+          make_map(&mg, grad_out, B, (int)(nd * nd), H, W, T::S2, T::TH, T::ND, gbs) &&
+          (out_act == nullptr || make_map(&ma, out_act, B, (int)(nd * nd), H, W, T::S2, T::TH, T::ND, gbs));
+    if (tma) {
+      const size_t gstage = sizeof(float) * T::ND * T::ND * T::TH * T::S2;  // coefficient staging, reused by ring + red
+      if (gstage > smem) smem = gstage;
+      auto kernel = corr_bwd_tiled<T, BWD_CR, STG_TMA>;
+      if (int e = set_smem(kernel, smem)) return e;
+      if (int e = launch_kernel(kernel, grid, T::THREADS + 32, smem, s, 1, m1, m2, mg, ma, grad_out, out_act, f1, f2, df1, df2, C, H, W, g_bstride,
+                                inv_c, leaky_slope, nmodes, first, ks)) return e;
     } else {
-      if (int e = set_smem(corr_bwd_tiled<T, BWD_CR, false>, smem)) return e;
-      corr_bwd_tiled<T, BWD_CR, false><<<grid, T::THREADS, smem, s>>>(grad_out, out_act, f1, f2, df1, df2, C, H, W, g_bstride,
-                                                                     inv_c, leaky_slope, nmodes, first);
+      auto kernel = vec ? corr_bwd_tiled<T, BWD_CR, STG_ASYNC16> : corr_bwd_tiled<T, BWD_CR, STG_ASYNC4>;
+      if (int e = set_smem(kernel, smem)) return e;
+      if (int e = launch_kernel(kernel, grid, T::THREADS, smem, s, 1, m1, m2, mg, ma, grad_out, out_act, f1, f2, df1, df2, C, H, W, g_bstride,
+                                inv_c, leaky_slope, nmodes, first, ks)) return e;
     }
   } else {
     dim3 grid((H * W + 127) / 128, C, B);

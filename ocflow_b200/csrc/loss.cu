@@ -189,64 +189,144 @@ gradient_kernel(const float* __restrict__ img, float* __restrict__ dx, float* __
 }
 
 // ---- fused occlusion-aware photometric pass -----------------------------------------------------
-__global__ void __launch_bounds__(LT)
+// A thread owns VPX consecutive pixels of one row (VPX = 4 when rows are 16-byte aligned: every regular stream --
+// flow, range map, img1, flow_gt, occ_gt, d_flow -- moves as 128-bit accesses and the 4*VPX*C tap gathers of img2 are
+// all in flight together; VPX = 1 is the ragged-width fallback).
+template <int VPX>
+struct PixVec {
+  float v[VPX];
+};
+
+template <int VPX>
+__device__ __forceinline__ PixVec<VPX> ld_vec(const float* p) {
+  PixVec<VPX> r;
+  if (VPX == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    r.v[0] = t.x; r.v[1 % VPX] = t.y; r.v[2 % VPX] = t.z; r.v[3 % VPX] = t.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < VPX; ++i) r.v[i] = p[i];
+  }
+  return r;
+}
+
+template <int VPX>
+__device__ __forceinline__ void st_vec(float* p, const PixVec<VPX>& r) {
+  if (VPX == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1 % VPX], r.v[2 % VPX], r.v[3 % VPX]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < VPX; ++i) p[i] = r.v[i];
+  }
+}
+
+// grid (blocks over the pixel groups of ONE image, B): 32-bit index math only, no 64-bit divisions.
+template <int VPX>
+__global__ void __launch_bounds__(LT, 2)
 occ_photo_fused_kernel(const float* __restrict__ img1, const float* __restrict__ img2, const float* __restrict__ flow,
                        const float* __restrict__ range, const float* __restrict__ flow_gt, const float* __restrict__ occ_gt,
                        double* __restrict__ sums, float* __restrict__ dflow, float* __restrict__ warped, int C, int H, int W,
-                       size_t npix, float a2) {
-  const size_t HW = (size_t)H * W;
+                       float a2) {
+  const int HW = H * W;
+  const int gpi = HW / VPX;  // pixel groups per image
+  const int b = blockIdx.y;
   float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const float fw = (float)(W - 1), fh = (float)(H - 1);
   const float dw = (float)max(W - 1, 1), dh = (float)max(H - 1, 1);
-  const size_t stride = (size_t)gridDim.x * LT;
-  for (size_t p = (size_t)blockIdx.x * LT + threadIdx.x; p < npix; p += stride) {
-    const size_t b = p / HW, q = p - b * HW;
-    const int y = (int)(q / W), x = (int)(q - (size_t)y * W);
-    const float u = flow[(b * 2) * HW + q], v = flow[(b * 2 + 1) * HW + q];
-    // align_corners=True coordinates, reference op order (models/model.py:211-212 + ATen unnormalize)
-    float ix = __fmul_rn(__fdiv_rn(__fadd_rn(__fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn((float)x, u)), dw), 1.0f), 1.0f), 2.0f), fw);
-    float iy = __fmul_rn(__fdiv_rn(__fadd_rn(__fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn((float)y, v)), dh), 1.0f), 1.0f), 2.0f), fh);
-    if (!(ix > -2147483648.0f && ix < 2147483520.0f)) ix = -100.f;
-    if (!(iy > -2147483648.0f && iy < 2147483520.0f)) iy = -100.f;
-    const float fx0 = floorf(ix), fy0 = floorf(iy);
-    const int x0 = (int)fx0, y0 = (int)fy0;
-    const float wx1 = ix - fx0, wx0 = (fx0 + 1.f) - ix, wy1 = iy - fy0, wy0 = (fy0 + 1.f) - iy;
-    const bool vx0 = x0 >= 0 && x0 < W, vx1 = x0 + 1 >= 0 && x0 + 1 < W;
-    const bool vy0 = y0 >= 0 && y0 < H, vy1 = y0 + 1 >= 0 && y0 + 1 < H;
-    const bool vnw = vx0 && vy0, vne = vx1 && vy0, vsw = vx0 && vy1, vse = vx1 && vy1;
-    const size_t onw = vnw ? (size_t)y0 * W + x0 : 0, one = vne ? (size_t)y0 * W + x0 + 1 : 0;
-    const size_t osw = vsw ? (size_t)(y0 + 1) * W + x0 : 0, ose = vse ? (size_t)(y0 + 1) * W + x0 + 1 : 0;
-    const float occ = range != nullptr ? 1.0f - fminf(fmaxf(range[p], 0.f), 1.f) : 0.f;
-    const float vis = 1.0f - occ;
-    float e = 0.f, gx = 0.f, gy = 0.f;
-    for (int c = 0; c < C; ++c) {
-      const float* ip = img2 + (b * C + c) * HW;
-      const float a = vnw ? ip[onw] : 0.f, bb = vne ? ip[one] : 0.f, cc = vsw ? ip[osw] : 0.f, dd = vse ? ip[ose] : 0.f;
-      float s = 0.f;
-      s = fmaf(a, wx0 * wy0, s); s = fmaf(bb, wx1 * wy0, s); s = fmaf(cc, wx0 * wy1, s); s = fmaf(dd, wx1 * wy1, s);
-      if (warped != nullptr) warped[(b * C + c) * HW + q] = s;
-      const float d = s - img1[(b * C + c) * HW + q];
-      const float r = rho(d, a2);
-      e += r;
-      const float gr = d / r;  // rho'
-      gx = fmaf(gr, (bb - a) * wy0 + (dd - cc) * wy1, gx);
-      gy = fmaf(gr, (cc - a) * wx0 + (dd - bb) * wx1, gy);
+  const float cx = (0.5f * fw) * (2.0f / dw), cy = (0.5f * fh) * (2.0f / dh);  // align_corners=True chain factor (== 1)
+  const float* fl_b = flow + (size_t)b * 2 * HW;
+  const float* i1_b = img1 + (size_t)b * C * HW;
+  const float* i2_b = img2 + (size_t)b * C * HW;
+  for (int gi = blockIdx.x * LT + threadIdx.x; gi < gpi; gi += gridDim.x * LT) {
+    const int q = gi * VPX;
+    const int y = q / W, x = q - y * W;
+    const PixVec<VPX> U = ld_vec<VPX>(fl_b + q), V = ld_vec<VPX>(fl_b + HW + q);
+    int onw[VPX], one[VPX], osw[VPX], ose[VPX];
+    float wx0[VPX], wx1[VPX], wy0[VPX], wy1[VPX];
+    bool vnw[VPX], vne[VPX], vsw[VPX], vse[VPX];
+#pragma unroll
+    for (int i = 0; i < VPX; ++i) {
+      // align_corners=True coordinates, reference op order (models/model.py:211-212 + ATen unnormalize); x*0.5f == x/2 exactly
+      float ix = __fmul_rn(__fmul_rn(__fadd_rn(__fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn((float)(x + i), U.v[i])), dw), 1.0f), 1.0f), 0.5f), fw);
+      float iy = __fmul_rn(__fmul_rn(__fadd_rn(__fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn((float)y, V.v[i])), dh), 1.0f), 1.0f), 0.5f), fh);
+      if (!(ix > -2147483648.0f && ix < 2147483520.0f)) ix = -100.f;
+      if (!(iy > -2147483648.0f && iy < 2147483520.0f)) iy = -100.f;
+      const float fx0 = floorf(ix), fy0 = floorf(iy);
+      const int x0 = (int)fx0, y0 = (int)fy0;
+      wx1[i] = ix - fx0; wx0[i] = (fx0 + 1.f) - ix; wy1[i] = iy - fy0; wy0[i] = (fy0 + 1.f) - iy;
+      const bool vx0 = x0 >= 0 && x0 < W, vx1 = x0 + 1 >= 0 && x0 + 1 < W;
+      const bool vy0 = y0 >= 0 && y0 < H, vy1 = y0 + 1 >= 0 && y0 + 1 < H;
+      vnw[i] = vx0 && vy0; vne[i] = vx1 && vy0; vsw[i] = vx0 && vy1; vse[i] = vx1 && vy1;
+      const int o = y0 * W + x0;
+      onw[i] = vnw[i] ? o : 0; one[i] = vne[i] ? o + 1 : 0; osw[i] = vsw[i] ? o + W : 0; ose[i] = vse[i] ? o + W + 1 : 0;
     }
-    acc[0] += e * vis; acc[1] += vis; acc[2] += e * occ; acc[3] += occ;
+    PixVec<VPX> occv, vis;
+    if (range != nullptr) {
+      const PixVec<VPX> r = ld_vec<VPX>(range + (size_t)b * HW + q);
+#pragma unroll
+      for (int i = 0; i < VPX; ++i) occv.v[i] = 1.0f - fminf(fmaxf(r.v[i], 0.f), 1.f);
+    } else {
+#pragma unroll
+      for (int i = 0; i < VPX; ++i) occv.v[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < VPX; ++i) vis.v[i] = 1.0f - occv.v[i];
+    float e[VPX], gx[VPX], gy[VPX];
+#pragma unroll
+    for (int i = 0; i < VPX; ++i) { e[i] = 0.f; gx[i] = 0.f; gy[i] = 0.f; }
+    for (int c = 0; c < C; ++c) {
+      const float* ip = i2_b + c * HW;
+      const PixVec<VPX> t1 = ld_vec<VPX>(i1_b + c * HW + q);
+      float a[VPX], bb[VPX], cc[VPX], dd[VPX];
+#pragma unroll
+      for (int i = 0; i < VPX; ++i) {
+        a[i] = vnw[i] ? __ldg(ip + onw[i]) : 0.f; bb[i] = vne[i] ? __ldg(ip + one[i]) : 0.f;
+        cc[i] = vsw[i] ? __ldg(ip + osw[i]) : 0.f; dd[i] = vse[i] ? __ldg(ip + ose[i]) : 0.f;
+      }
+      PixVec<VPX> wv;
+#pragma unroll
+      for (int i = 0; i < VPX; ++i) {
+        float s = 0.f;
+        s = fmaf(a[i], wx0[i] * wy0[i], s); s = fmaf(bb[i], wx1[i] * wy0[i], s);
+        s = fmaf(cc[i], wx0[i] * wy1[i], s); s = fmaf(dd[i], wx1[i] * wy1[i], s);
+        wv.v[i] = s;
+        const float d = s - t1.v[i];
+        const float r2 = fmaf(d, d, a2);
+        const float inv = rsqrtf(r2);     // rho = r2 * inv, rho' = d * inv   (MUFU.RSQ, <= 2 ulp: far inside the loss tolerance)
+        e[i] = fmaf(r2, inv, e[i]);
+        const float gr = d * inv;
+        gx[i] = fmaf(gr, (bb[i] - a[i]) * wy0[i] + (dd[i] - cc[i]) * wy1[i], gx[i]);
+        gy[i] = fmaf(gr, (cc[i] - a[i]) * wx0[i] + (dd[i] - bb[i]) * wx1[i], gy[i]);
+      }
+      if (warped != nullptr) st_vec<VPX>(warped + ((size_t)b * C + c) * HW + q, wv);
+    }
+#pragma unroll
+    for (int i = 0; i < VPX; ++i) {
+      acc[0] += e[i] * vis.v[i]; acc[1] += vis.v[i]; acc[2] += e[i] * occv.v[i]; acc[3] += occv.v[i];
+    }
     if (dflow != nullptr) {
-      // align_corners=True chain factor: (W-1)/2 * 2/max(W-1,1)
-      dflow[(b * 2) * HW + q] = gx * vis * (0.5f * fw) * (2.0f / dw);
-      dflow[(b * 2 + 1) * HW + q] = gy * vis * (0.5f * fh) * (2.0f / dh);
+      PixVec<VPX> ox, oy;
+#pragma unroll
+      for (int i = 0; i < VPX; ++i) { ox.v[i] = gx[i] * vis.v[i] * cx; oy.v[i] = gy[i] * vis.v[i] * cy; }
+      st_vec<VPX>(dflow + (size_t)b * 2 * HW + q, ox);
+      st_vec<VPX>(dflow + (size_t)b * 2 * HW + HW + q, oy);
     }
     if (flow_gt != nullptr) {
-      const float du = u - flow_gt[(b * 2) * HW + q], dv = v - flow_gt[(b * 2 + 1) * HW + q];
-      acc[4] += du * du + dv * dv;
+      const PixVec<VPX> gu = ld_vec<VPX>(flow_gt + (size_t)b * 2 * HW + q), gv = ld_vec<VPX>(flow_gt + (size_t)b * 2 * HW + HW + q);
+#pragma unroll
+      for (int i = 0; i < VPX; ++i) {
+        const float du = U.v[i] - gu.v[i], dv = V.v[i] - gv.v[i];
+        acc[4] += du * du + dv * dv;
+      }
     }
     if (occ_gt != nullptr) {
       // F.binary_cross_entropy(input=occ_gt, target=occ_pred)  -- swapped on purpose, models/model.py:407
-      const float pin = occ_gt[p];
-      const float lp = fmaxf(logf(pin), -100.f), l1p = fmaxf(logf(1.0f - pin), -100.f);
-      acc[5] += -(occ * lp + (1.0f - occ) * l1p);
+      const PixVec<VPX> pin = ld_vec<VPX>(occ_gt + (size_t)b * HW + q);
+#pragma unroll
+      for (int i = 0; i < VPX; ++i) {
+        const float lp = fmaxf(logf(pin.v[i]), -100.f), l1p = fmaxf(logf(1.0f - pin.v[i]), -100.f);
+        acc[5] += -(occv.v[i] * lp + (1.0f - occv.v[i]) * l1p);
+      }
     }
   }
   ocf_block_accumulate<6>(acc, sums);
@@ -381,8 +461,22 @@ extern "C" int ocf_occ_photo_fused(const float* img1, const float* img2, const f
   cudaError_t e = cudaMemsetAsync(sums, 0, 8 * sizeof(double), s);
   if (e != cudaSuccess) return (int)e;
   const size_t npix = (size_t)B * H * W;
-  occ_photo_fused_kernel<<<stream_grid(npix), LT, 0, s>>>(img1, img2, flow, range_map, flow_gt, occ_gt, sums, dflow_unit, warped_out,
-                                                          C, H, W, npix, alpha * alpha);
+  bool vec = (W % 4 == 0) && ocf_aligned16(img1) && ocf_aligned16(flow);
+  const float* opt[5] = {range_map, flow_gt, occ_gt, dflow_unit, warped_out};
+  for (const float* p : opt) vec = vec && (p == nullptr || ocf_aligned16(p));
+  OCF_REQUIRE((long long)C * H * W < (1LL << 31) && B <= 65535, OCF_EUNSUPPORTED);
+  const int vpx = vec ? 4 : 1;
+  const int gpi = H * W / vpx;
+  // blocks per image: whole grid ~ 2 CTAs x 148 SMs x 2 waves, each thread doing >= 1 group
+  int bx = (gpi + LT - 1) / LT;
+  const int cap = (4 * OCF_SM_COUNT + B - 1) / B;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, B);
+  if (vec)
+    occ_photo_fused_kernel<4><<<grid, LT, 0, s>>>(img1, img2, flow, range_map, flow_gt, occ_gt, sums, dflow_unit, warped_out, C, H, W, alpha * alpha);
+  else
+    occ_photo_fused_kernel<1><<<grid, LT, 0, s>>>(img1, img2, flow, range_map, flow_gt, occ_gt, sums, dflow_unit, warped_out, C, H, W, alpha * alpha);
   return ocf_launch_status();
 }
 

@@ -97,88 +97,134 @@ warp_fwd_kernel(const float* __restrict__ img, const float* __restrict__ flow, c
   }
 }
 
-// Backward.  d_img is a scatter (red.global.add.f32, zeroed by the caller entry point); d_flow / d_occ are
-// per-pixel and accumulated across channel slabs with one atomic per slab (plain store when 1 slab).
-// Neighbouring lanes usually hit neighbouring taps; merging the east tap of lane l with the west
-// tap of lane l+1 in registers halves the atomics (warp-aggregated scatter).
+// Backward.  d_img is a scatter (red.global.add.f32, zeroed by the entry point); d_flow / d_occ are per-pixel and
+// accumulated across channel slabs with one atomic per slab (plain store when there is 1 slab).
+// Warp-aggregated scatter: a thread owns R vertically adjacent pixels and a warp 32 horizontally adjacent columns.
+// For a smooth flow the south taps of row r are the north taps of row r+1 and the east taps of lane l are the west
+// taps of lane l+1; both coincidences are detected once per pixel (they do not depend on the channel) and the
+// contributions are summed in registers / with one shuffle before the atomic, so a fully coherent neighbourhood
+// issues (R+1)/R atomics per pixel and channel instead of 4.
+template <int R>
 __global__ void __launch_bounds__(WARP_THREADS)
 warp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ img, const float* __restrict__ flow,
                 const float* __restrict__ occ, float* __restrict__ d_img, float* __restrict__ d_flow,
                 float* __restrict__ d_occ, int C, int H, int W, int slab, int nslabs, int flags, float scale) {
-  const int pix = blockIdx.x * WARP_THREADS + threadIdx.x;
   const int HW = H * W;
-  const bool active = pix < HW;
-  const int pixc = active ? pix : HW - 1;
-  const int y = pixc / W, x = pixc - y * W;
+  const int HG = (H + R - 1) / R;  // row groups
+  const int gidx = blockIdx.x * WARP_THREADS + threadIdx.x;
+  const bool in_grid = gidx < HG * W;
+  const int gc = in_grid ? gidx : HG * W - 1;
+  const int yg = gc / W, x = gc - yg * W;
   const int b = blockIdx.z;
   const bool align = flags & OCF_WARP_ALIGN_CORNERS;
-  const float u = __fmul_rn(__ldg(flow + ((size_t)b * 2) * HW + pixc), scale);
-  const float v = __fmul_rn(__ldg(flow + ((size_t)b * 2 + 1) * HW + pixc), scale);
-  const float ix = unnormalize(__fadd_rn((float)x, u), W, max(W - 1, 1), align);
-  const float iy = unnormalize(__fadd_rn((float)y, v), H, max(H - 1, 1), align);
-  const Taps t = make_taps(ix, iy, H, W);
-  float mul = active ? 1.f : 0.f;
-  if (flags & OCF_WARP_IS_MASK) mul *= mask_of(t);
-  float occv = 1.f;
-  if (occ != nullptr) occv = __ldg(occ + (size_t)b * HW + pixc);
-  const float gmul = mul * occv;  // d out / d sample
-  const float wnw = t.wx0 * t.wy0, wne = t.wx1 * t.wy0, wsw = t.wx0 * t.wy1, wse = t.wx1 * t.wy1;
-  const bool vnw = t.vx0 && t.vy0, vne = t.vx1 && t.vy0, vsw = t.vx0 && t.vy1, vse = t.vx1 && t.vy1;
-  const int onw = vnw ? t.y0 * W + t.x0 : 0, one = vne ? t.y0 * W + t.x0 + 1 : 0;
-  const int osw = vsw ? (t.y0 + 1) * W + t.x0 : 0, ose = vse ? (t.y0 + 1) * W + t.x0 + 1 : 0;
-
-  // lane-neighbour merge plan (channel independent): my west taps can absorb the previous lane's east
-  // taps when they are the same address and both valid.
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const int prev_one = __shfl_up_sync(full, vne ? one : -1, 1);
-  const int prev_ose = __shfl_up_sync(full, vse ? ose : -1, 1);
-  const bool take_n = lane > 0 && vnw && prev_one == onw;   // I add prev lane's NE into my NW
-  const bool take_s = lane > 0 && vsw && prev_ose == osw;
-  const bool give_n = __shfl_down_sync(full, (int)take_n, 1) && lane < 31;  // my NE is absorbed by next lane
-  const bool give_s = __shfl_down_sync(full, (int)take_s, 1) && lane < 31;
+
+  int pix[R];
+  bool act[R];
+  float wnw[R], wne[R], wsw[R], wse[R], wx0[R], wx1[R], wy0[R], wy1[R], gmul[R], mul[R];
+  int onw[R], one[R], osw[R], ose[R];  // -1 when the tap is dropped
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int y = yg * R + r;
+    act[r] = in_grid && y < H;
+    const int yc = min(y, H - 1);
+    pix[r] = yc * W + x;
+    const float u = __fmul_rn(__ldg(flow + ((size_t)b * 2) * HW + pix[r]), scale);
+    const float v = __fmul_rn(__ldg(flow + ((size_t)b * 2 + 1) * HW + pix[r]), scale);
+    const float ix = unnormalize(__fadd_rn((float)x, u), W, max(W - 1, 1), align);
+    const float iy = unnormalize(__fadd_rn((float)yc, v), H, max(H - 1, 1), align);
+    const Taps t = make_taps(ix, iy, H, W);
+    mul[r] = act[r] ? 1.f : 0.f;
+    if (flags & OCF_WARP_IS_MASK) mul[r] *= mask_of(t);
+    const float occv = occ != nullptr ? __ldg(occ + (size_t)b * HW + pix[r]) : 1.f;
+    gmul[r] = mul[r] * occv;  // d out / d sample
+    wx0[r] = t.wx0; wx1[r] = t.wx1; wy0[r] = t.wy0; wy1[r] = t.wy1;
+    wnw[r] = t.wx0 * t.wy0; wne[r] = t.wx1 * t.wy0; wsw[r] = t.wx0 * t.wy1; wse[r] = t.wx1 * t.wy1;
+    const int o = t.y0 * W + t.x0;
+    onw[r] = (act[r] && t.vx0 && t.vy0) ? o : -1;
+    one[r] = (act[r] && t.vx1 && t.vy0) ? o + 1 : -1;
+    osw[r] = (act[r] && t.vx0 && t.vy1) ? o + W : -1;
+    ose[r] = (act[r] && t.vx1 && t.vy1) ? o + W + 1 : -1;
+  }
+  // merge plan (channel independent)
+  bool mvw[R], mve[R], emit_sw[R], emit_se[R], take_n[R], give_n[R], take_s[R], give_s[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    mvw[r] = r > 0 && onw[r] >= 0 && onw[r] == osw[r - 1];   // north-west tap of row r absorbs south-west of row r-1
+    mve[r] = r > 0 && one[r] >= 0 && one[r] == ose[r - 1];
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    emit_sw[r] = osw[r] >= 0 && !(r + 1 < R && mvw[r + 1]);
+    emit_se[r] = ose[r] >= 0 && !(r + 1 < R && mve[r + 1]);
+    const int pne = __shfl_up_sync(full, one[r], 1);
+    const int pse = __shfl_up_sync(full, emit_se[r] ? ose[r] : -1, 1);
+    take_n[r] = lane > 0 && onw[r] >= 0 && pne == onw[r];
+    take_s[r] = lane > 0 && emit_sw[r] && pse == osw[r];
+    give_n[r] = __shfl_down_sync(full, (int)take_n[r], 1) && lane < 31;
+    give_s[r] = __shfl_down_sync(full, (int)take_s[r], 1) && lane < 31;
+  }
 
   const int c_begin = blockIdx.y * slab, c_end = min(C, c_begin + slab);
   const float* ip = img + ((size_t)b * C + c_begin) * HW;
-  const float* gp = gout + ((size_t)b * C + c_begin) * HW + pixc;
+  const float* gp = gout + ((size_t)b * C + c_begin) * HW;
   float* dp = d_img != nullptr ? d_img + ((size_t)b * C + c_begin) * HW : nullptr;
-  float gx = 0.f, gy = 0.f, go = 0.f;
+  float gx[R], gy[R], go[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) { gx[r] = 0.f; gy[r] = 0.f; go[r] = 0.f; }
   const bool need_vals = d_flow != nullptr || d_occ != nullptr;
+#pragma unroll 2
   for (int c = c_begin; c < c_end; ++c, ip += HW, gp += HW) {
-    const float graw = active ? __ldg(gp) : 0.f;
-    const float g = graw * gmul;
-    if (need_vals) {
-      const float a = vnw ? __ldg(ip + onw) : 0.f, bb = vne ? __ldg(ip + one) : 0.f;
-      const float cc = vsw ? __ldg(ip + osw) : 0.f, dd = vse ? __ldg(ip + ose) : 0.f;
-      // ATen grid_sampler_2d_backward: gix -= nw*(iy_se-iy) ; += ne*(iy_sw-iy) ; -= sw*(iy-iy_ne) ; += se*(iy-iy_nw)
-      gx += g * ((bb - a) * t.wy0 + (dd - cc) * t.wy1);
-      gy += g * ((cc - a) * t.wx0 + (dd - bb) * t.wx1);
-      if (d_occ != nullptr) go += graw * mul * (a * wnw + bb * wne + cc * wsw + dd * wse);
+    float cnw[R], cne[R], csw[R], cse[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float graw = act[r] ? __ldg(gp + pix[r]) : 0.f;
+      const float g = graw * gmul[r];
+      if (need_vals) {
+        const float a = onw[r] >= 0 ? __ldg(ip + onw[r]) : 0.f, bb = one[r] >= 0 ? __ldg(ip + one[r]) : 0.f;
+        const float cc = osw[r] >= 0 ? __ldg(ip + osw[r]) : 0.f, dd = ose[r] >= 0 ? __ldg(ip + ose[r]) : 0.f;
+        // ATen grid_sampler_2d_backward: gix -= nw*(iy_se-iy) ; += ne*(iy_sw-iy) ; -= sw*(iy-iy_ne) ; += se*(iy-iy_nw)
+        gx[r] += g * ((bb - a) * wy0[r] + (dd - cc) * wy1[r]);
+        gy[r] += g * ((cc - a) * wx0[r] + (dd - bb) * wx1[r]);
+        if (d_occ != nullptr) go[r] += graw * mul[r] * (a * wnw[r] + bb * wne[r] + cc * wsw[r] + dd * wse[r]);
+      }
+      cnw[r] = g * wnw[r]; cne[r] = g * wne[r]; csw[r] = g * wsw[r]; cse[r] = g * wse[r];
     }
     if (dp != nullptr) {
-      float cnw = g * wnw, cne = g * wne, csw = g * wsw, cse = g * wse;
-      const float pn = __shfl_up_sync(full, cne, 1), ps = __shfl_up_sync(full, cse, 1);
-      if (take_n) cnw += pn;
-      if (take_s) csw += ps;
-      if (vnw) atomicAdd(dp + onw, cnw);
-      if (vne && !give_n) atomicAdd(dp + one, cne);
-      if (vsw) atomicAdd(dp + osw, csw);
-      if (vse && !give_s) atomicAdd(dp + ose, cse);
+#pragma unroll
+      for (int r = 1; r < R; ++r) {
+        if (mvw[r]) cnw[r] += csw[r - 1];
+        if (mve[r]) cne[r] += cse[r - 1];
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float pn = __shfl_up_sync(full, cne[r], 1), ps = __shfl_up_sync(full, cse[r], 1);
+        if (take_n[r]) cnw[r] += pn;
+        if (take_s[r]) csw[r] += ps;
+        if (onw[r] >= 0) atomicAdd(dp + onw[r], cnw[r]);
+        if (one[r] >= 0 && !give_n[r]) atomicAdd(dp + one[r], cne[r]);
+        if (emit_sw[r]) atomicAdd(dp + osw[r], csw[r]);
+        if (emit_se[r] && !give_s[r]) atomicAdd(dp + ose[r], cse[r]);
+      }
       dp += HW;
     }
   }
-  if (!active) return;
-  if (d_flow != nullptr) {
-    // chain: ATen multiplies by (W-1)/2 resp. W/2, the reference's normalisation by 2/max(W-1,1)
-    const float mx = (align ? 0.5f * (float)(W - 1) : 0.5f * (float)W) * (2.0f / (float)max(W - 1, 1)) * scale;
-    const float my = (align ? 0.5f * (float)(H - 1) : 0.5f * (float)H) * (2.0f / (float)max(H - 1, 1)) * scale;
-    float* fx = d_flow + ((size_t)b * 2) * HW + pix;
-    if (nslabs == 1) { fx[0] = gx * mx; fx[HW] = gy * my; }
-    else { atomicAdd(fx, gx * mx); atomicAdd(fx + HW, gy * my); }
-  }
-  if (d_occ != nullptr) {
-    float* po = d_occ + (size_t)b * HW + pix;
-    if (nslabs == 1) *po = go; else atomicAdd(po, go);
+  // chain: ATen multiplies by (W-1)/2 resp. W/2, the reference's normalisation by 2/max(W-1,1)
+  const float mx = (align ? 0.5f * (float)(W - 1) : 0.5f * (float)W) * (2.0f / (float)max(W - 1, 1)) * scale;
+  const float my = (align ? 0.5f * (float)(H - 1) : 0.5f * (float)H) * (2.0f / (float)max(H - 1, 1)) * scale;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (!act[r]) continue;
+    if (d_flow != nullptr) {
+      float* fx = d_flow + ((size_t)b * 2) * HW + pix[r];
+      if (nslabs == 1) { fx[0] = gx[r] * mx; fx[HW] = gy[r] * my; }
+      else { atomicAdd(fx, gx[r] * mx); atomicAdd(fx + HW, gy[r] * my); }
+    }
+    if (d_occ != nullptr) {
+      float* po = d_occ + (size_t)b * HW + pix[r];
+      if (nslabs == 1) *po = go[r]; else atomicAdd(po, go[r]);
+    }
   }
 }
 
@@ -283,8 +329,9 @@ extern "C" int ocf_warp_bwd(const float* grad_out, const float* img, const float
     if (d_flow != nullptr && (e = cudaMemsetAsync(d_flow, 0, sizeof(float) * (size_t)B * 2 * HW, s)) != cudaSuccess) return (int)e;
     if (d_occ != nullptr && (e = cudaMemsetAsync(d_occ, 0, sizeof(float) * (size_t)B * HW, s)) != cudaSuccess) return (int)e;
   }
-  dim3 grid((HW + WARP_THREADS - 1) / WARP_THREADS, nslabs, B);
-  warp_bwd_kernel<<<grid, WARP_THREADS, 0, s>>>(grad_out, img, flow, occ, d_img, d_flow, d_occ, C, H, W, slab, nslabs, flags, scale);
+  constexpr int R = 2;
+  dim3 grid(((H + R - 1) / R * W + WARP_THREADS - 1) / WARP_THREADS, nslabs, B);
+  warp_bwd_kernel<R><<<grid, WARP_THREADS, 0, s>>>(grad_out, img, flow, occ, d_img, d_flow, d_occ, C, H, W, slab, nslabs, flags, scale);
   return ocf_launch_status();
 }
 
