@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-roofline", action="store_true")
     ap.add_argument("--kernels-only", action="store_true", help="only time the hot-path kernels alone (developer aid)")
+    ap.add_argument("--cuda-profiler-range", action="store_true",
+                    help="bracket the timed region with cudaProfilerStart/Stop (use with ncu --profile-from-start off)")
     ap.add_argument("--levels", default="", help="kernels-only: comma list of C:h:w overriding the pyramid levels (e.g. 16:188:621)")
     return ap.parse_args()
 
@@ -320,11 +322,15 @@ def main():
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l1 = _lib.launch_count
+        if args.cuda_profiler_range:
+            torch.cuda.profiler.start()
         e0.record()
         for _ in range(args.steps):
             loss = step.step(batch)
         e1.record()
         barrier()
+        if args.cuda_profiler_range:
+            torch.cuda.profiler.stop()
         dt = e0.elapsed_time(e1) * 1e-3
         if not args.graph:
             per_step_launches = (_lib.launch_count - l1) // max(args.steps, 1)

@@ -73,8 +73,8 @@ int ocf_corr_bwd(const float* grad_out, const float* out_act, const float* f1, c
  *   moments_across_channels, moments_across_images)  models/networks/correlation_layer.py:42-82.
  *   All T tensors of the list must share one shape [B,C,H,W] (they do at every call site).
  *   flags: bit0 normalize, bit1 center, bit2 moments_across_channels, bit3 moments_across_images.
- *   stats workspace (device, caller-owned): 2*T*B*G floats of per-group {mean, var} followed by
- *   2*T*B*G floats of the {mean, inv_std} actually applied, G = 1 (across channels) or C.
+ *   stats workspace (device, caller-owned, 8-byte aligned): 8*T*B*G floats, G = 1 (across channels) or C
+ *   -- fp64 partial sums, then per-group {mean, var}, then the {mean, inv_std} actually applied.
  * ------------------------------------------------------------------------------------------- */
 #define OCF_NORM_NORMALIZE 1
 #define OCF_NORM_CENTER 2
@@ -83,7 +83,7 @@ int ocf_corr_bwd(const float* grad_out, const float* out_act, const float* f1, c
 int ocf_normalize_fwd(const float* const* xs, float* const* ys, int T, int B, int C, int H, int W,
                       int flags, float* stats, ocf_stream_t stream);
 /* grads wrt every input, differentiating through the statistics (no detach in the reference).
- * red workspace: 2*T*B*G floats. */
+ * red workspace (8-byte aligned): 8*T*B*G floats. */
 int ocf_normalize_bwd(const float* const* grad_ys, const float* const* xs, float* const* grad_xs,
                       int T, int B, int C, int H, int W, int flags, const float* stats, float* red,
                       ocf_stream_t stream);

@@ -644,11 +644,19 @@ int set_smem(K kernel, size_t bytes) {
   return 0;
 }
 
-// channel split: enough CTAs to cover the 148 SMs twice, at least `min_ch` channels per CTA, power of two <= 8
-int pick_ksplit(long long tiles, int C, int min_ch) {
-  int ks = 1;
-  while (ks < 8 && tiles * ks < 2LL * OCF_SM_COUNT && C / (ks * 2) >= min_ch) ks *= 2;
-  return ks;
+// Channel split factor (power of two <= 8).  Cost model in units of one full-tile CTA: ceil(tiles*ks / slots) rounds of
+// 1/ks tile each, plus a fixed allowance for the DSMEM reduction when ks > 1; at least `min_ch` channels per CTA.
+int pick_ksplit(long long tiles, int C, int min_ch, bool reduce_cost = true) {
+  const long long slots = 2LL * OCF_SM_COUNT;  // 2 resident CTAs per SM
+  int best = 1;
+  double best_cost = 1e30;
+  for (int ks = 1; ks <= 8; ks *= 2) {
+    if (ks > 1 && C / ks < min_ch) break;
+    const long long rounds = (tiles * ks + slots - 1) / slots;
+    const double cost = (double)rounds / ks + ((ks > 1 && reduce_cost) ? 0.15 : 0.02 * (ks > 1));
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = ks; }
+  }
+  return best;
 }
 
 template <class K, class... Args>
@@ -756,7 +764,7 @@ extern "C" int ocf_corr_bwd(const float* grad_out, const float* out_act, const f
     const int nmodes = (df1 != nullptr && df2 != nullptr) ? 2 : 1;
     const int first = df1 != nullptr ? 0 : 1;
     const int gx = (W + T::TW - 1) / T::TW, gy = (H + T::TH - 1) / T::TH;
-    const int ks = pick_ksplit((long long)gx * gy * B * nmodes, C, 2 * T::CC);
+    const int ks = pick_ksplit((long long)gx * gy * B * nmodes, C, 2 * T::CC, false);
     dim3 grid(gx, gy, B * nmodes * ks);
     const bool vec = (W % 4 == 0) && ocf_aligned16(f1) && ocf_aligned16(f2) && (df1 == nullptr || ocf_aligned16(df1)) &&
                      (df2 == nullptr || ocf_aligned16(df2));
