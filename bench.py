@@ -209,6 +209,19 @@ def kernel_table(args, torch):
             "ocf_corr_fwd", P(f1), P(f2), P(out), B, C, h, w, 4, 0, 0.1, None, st), 4 * n * (2 * C + 81), 2)
         table["corr_bwd_L%d" % lvl] = (lambda gout=gout, out=out, f1=f1, f2=f2, d1=d1, d2=d2, C=C, h=h, w=w: _lib.call(
             "ocf_corr_bwd", P(gout), P(out), P(f1), P(f2), P(d1), P(d2), B, C, h, w, 4, 0, 0.1, st), 4 * n * (81 + 4 * C), 1)
+        # normalisation of the two feature maps of the level (3 kernels fwd, 3 kernels bwd)
+        y1, y2 = torch.empty_like(f1), torch.empty_like(f2)
+        stats = torch.empty(8 * 2 * B, device=dev)
+        red = torch.empty(8 * 2 * B, device=dev)
+        xs_arr = (ctypes.c_void_p * 2)(f1.data_ptr(), f2.data_ptr())
+        ys_arr = (ctypes.c_void_p * 2)(y1.data_ptr(), y2.data_ptr())
+        gs_arr = (ctypes.c_void_p * 2)(d1.data_ptr(), d2.data_ptr())
+        table["normalize_fwd_L%d" % lvl] = (lambda xs_arr=xs_arr, ys_arr=ys_arr, stats=stats, C=C, h=h, w=w: _lib.call(
+            "ocf_normalize_fwd", ctypes.cast(xs_arr, ctypes.c_void_p), ctypes.cast(ys_arr, ctypes.c_void_p), 2, B, C, h, w, 15, P(stats), st),
+            4 * n * 2 * C * 3, 2)
+        table["normalize_bwd_L%d" % lvl] = (lambda xs_arr=xs_arr, ys_arr=ys_arr, gs_arr=gs_arr, stats=stats, red=red, C=C, h=h, w=w: _lib.call(
+            "ocf_normalize_bwd", ctypes.cast(ys_arr, ctypes.c_void_p), ctypes.cast(xs_arr, ctypes.c_void_p), ctypes.cast(gs_arr, ctypes.c_void_p),
+            2, B, C, h, w, 15, P(stats), P(red), st), 4 * n * 2 * C * 4, 1)
         if lvl < 6 or custom:
             table["warp_fwd_L%d" % lvl] = (lambda f2=f2, fl=fl, wout=wout, C=C, h=h, w=w: _lib.call(
                 "ocf_warp_fwd", P(f2), P(fl), None, P(wout), B, C, h, w, 0, 1.25, st), 4 * n * (2 * C + 2), 2)

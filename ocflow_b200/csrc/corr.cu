@@ -28,6 +28,7 @@
 #include <cooperative_groups.h>
 #include <cuda.h>  // CUtensorMap types only; the driver entry point is fetched at run time (no libcuda link dependency)
 
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -168,7 +169,7 @@ __device__ __forceinline__ ChunkRange chunk_range(int C, int CC, int ksplit, int
 // ---- forward ------------------------------------------------------------------------------------
 // grid (tiles_x, tiles_y, B * ksplit); when ksplit > 1 the launch carries cluster dims (1, 1, ksplit).
 template <class T, int STG>
-__global__ void __launch_bounds__(Threads<T, STG>::value, 2)
+__global__ void __launch_bounds__(T::THREADS, 2)
 corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2, const float* __restrict__ f1,
                const float* __restrict__ f2, float* __restrict__ out, int C, int H, int W, long long out_bstride, float inv_c,
                float slope, int ksplit) {
@@ -182,7 +183,7 @@ corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
   const int tid = threadIdx.x;
   const int lane = tid % T::LANES;
   const int tx = lane % T::TXT, ty = lane / T::TXT;
-  const int dyi = tid / T::LANES;  // == ND for the TMA producer warp
+  const int dyi = tid / T::LANES;
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
   const int b = blockIdx.z / ksplit, ks = blockIdx.z - b * ksplit;
   const ChunkRange cr = chunk_range(C, CC, ksplit, ks);
@@ -197,7 +198,7 @@ corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
   auto compute = [&](const float* st) {
     const float* p1 = st + ty * S1 + tx * PX;
     const float* p2 = st + T::F1_STAGE + (ty + dyi) * S2 + tx * PX;
-#pragma unroll 2
+#pragma unroll
     for (int c = 0; c < CC; ++c) {
       float a[PX], w[WIN];
 #pragma unroll
@@ -218,32 +219,34 @@ corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
   };
 
   if constexpr (TMA) {
+    // thread 0 doubles as the TMA producer (no extra warp: 288 threads leave 112 registers per thread at 2 CTAs/SM)
+    constexpr unsigned BYTES = sizeof(float) * STAGE;
+    auto issue_tma = [&](int i) {
+      const int s = i % STAGES;
+      float* st = smem + s * STAGE;
+      const int c0 = (cr.begin + i) * CC;
+      mbar_expect_tx(&full_bar[s], BYTES);
+      tma_load_4d(st, &map1, &full_bar[s], x0, y0, c0, b);
+      tma_load_4d(st + T::F1_STAGE, &map2, &full_bar[s], x0 - D, y0 - D, c0, b);
+    };
     if (tid == 0) {
 #pragma unroll
       for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ND); }
       mbar_fence_init();
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s)
+        if (s < nchunks) issue_tma(s);
     }
     __syncthreads();
-    if (dyi == ND) {  // producer warp: one elected lane feeds the ring
-      if (lane == 0) {
-        constexpr unsigned BYTES = sizeof(float) * STAGE;
-        for (int i = 0; i < nchunks; ++i) {
-          const int s = i % STAGES;
-          if (i >= STAGES) mbar_wait(&empty_bar[s], ((i / STAGES) - 1) & 1);
-          float* st = smem + s * STAGE;
-          const int c0 = (cr.begin + i) * CC;
-          mbar_expect_tx(&full_bar[s], BYTES);
-          tma_load_4d(st, &map1, &full_bar[s], x0, y0, c0, b);
-          tma_load_4d(st + T::F1_STAGE, &map2, &full_bar[s], x0 - D, y0 - D, c0, b);
-        }
-      }
-    } else {
-      for (int i = 0; i < nchunks; ++i) {
-        const int s = i % STAGES;
-        mbar_wait(&full_bar[s], (i / STAGES) & 1);
-        compute(smem + s * STAGE);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
+    for (int i = 0; i < nchunks; ++i) {
+      const int s = i % STAGES;
+      mbar_wait(&full_bar[s], (i / STAGES) & 1);
+      compute(smem + s * STAGE);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+      if (tid == 0 && i + STAGES < nchunks) {  // refill this stage as soon as all 9 warps have released it
+        mbar_wait(&empty_bar[s], (i / STAGES) & 1);
+        issue_tma(i + STAGES);
       }
     }
   } else {
@@ -274,7 +277,7 @@ corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
   constexpr bool VEC = STG != STG_ASYNC4;
   if (ksplit == 1) {
     const int y = y0 + ty, xs = x0 + tx * PX;
-    if (dyi >= ND || y >= H || xs >= W) return;
+    if (y >= H || xs >= W) return;
     float* ob = out + (size_t)b * bstride + ((size_t)(dyi * ND) * H + y) * W + xs;
 #pragma unroll
     for (int dx = 0; dx < ND; ++dx) {
@@ -303,7 +306,7 @@ corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
   __syncthreads();  // every warp is done reading the staging ring; reuse it as the partial tile [ND*ND][TH][S1]
   float* part = smem;
   static_assert(T::STAGES * STAGE >= ND * ND * TH * S1, "staging ring too small to hold the partial cost volume tile");
-  if (dyi < ND) {
+  {
 #pragma unroll
     for (int dx = 0; dx < ND; ++dx) {
       float* pp = part + ((dyi * ND + dx) * TH + ty) * S1 + tx * PX;
@@ -313,31 +316,39 @@ corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
     }
   }
   cluster.sync();
-  // rank r finalises planes k = r, r + ksplit, ...
+  // rank r finalises planes k = r, r + ksplit, ...: all (plane, row, float4) items are spread over the whole CTA and the
+  // ksplit peer reads of an item are issued together (independent DSMEM loads, ~215 cycles each)
   const unsigned rank = cluster.block_rank();
-  constexpr int ROW4 = TW / 4;
-  for (int k = (int)rank; k < ND * ND; k += ksplit) {
-    for (int i = tid; i < TH * ROW4; i += blockDim.x) {
-      const int ry = i / ROW4, x4 = i - ry * ROW4;
-      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int q = 0; q < ksplit; ++q) {
-        const float* peer = cluster.map_shared_rank(part, q);
-        const float4 v = *reinterpret_cast<const float4*>(peer + (k * TH + ry) * S1 + x4 * 4);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-      }
-      const int y = y0 + ry, x = x0 + x4 * 4;
-      if (y < H && x < W) {
-        float r[4] = {s.x * inv_c, s.y * inv_c, s.z * inv_c, s.w * inv_c};
+  constexpr int ROW4 = TW / 4, PLANE4 = TH * ROW4;
+  const int nplanes = (ND * ND - (int)rank + ksplit - 1) / ksplit;
+  const float* peers[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) r[j] = r[j] > 0.f ? r[j] : r[j] * slope;
-        float* o = out + (size_t)b * bstride + ((size_t)k * H + y) * W + x;
-        if (VEC) {
-          *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
-        } else {
+  for (int q = 0; q < 8; ++q) peers[q] = cluster.map_shared_rank(part, q < ksplit ? q : 0);
+  for (int it = tid; it < nplanes * PLANE4; it += blockDim.x) {
+    const int kp = it / PLANE4, i = it - kp * PLANE4;
+    const int k = (int)rank + kp * ksplit;
+    const int ry = i / ROW4, x4 = i - ry * ROW4;
+    const int off = (k * TH + ry) * S1 + x4 * 4;
+    float4 v[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (x + j < W) o[j] = r[j];
-        }
+    for (int q = 0; q < 8; ++q)
+      if (q < ksplit) v[q] = *reinterpret_cast<const float4*>(peers[q] + off);
+    float4 s = v[0];
+#pragma unroll
+    for (int q = 1; q < 8; ++q)
+      if (q < ksplit) { s.x += v[q].x; s.y += v[q].y; s.z += v[q].z; s.w += v[q].w; }
+    const int y = y0 + ry, x = x0 + x4 * 4;
+    if (y < H && x < W) {
+      float r[4] = {s.x * inv_c, s.y * inv_c, s.z * inv_c, s.w * inv_c};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[j] = r[j] > 0.f ? r[j] : r[j] * slope;
+      float* o = out + (size_t)b * bstride + ((size_t)k * H + y) * W + x;
+      if (VEC) {
+        *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (x + j < W) o[j] = r[j];
       }
     }
   }
@@ -647,13 +658,17 @@ int set_smem(K kernel, size_t bytes) {
 // Channel split factor (power of two <= 8).  Cost model in units of one full-tile CTA: ceil(tiles*ks / slots) rounds of
 // 1/ks tile each, plus a fixed allowance for the DSMEM reduction when ks > 1; at least `min_ch` channels per CTA.
 int pick_ksplit(long long tiles, int C, int min_ch, bool reduce_cost = true) {
+  if (const char* e = getenv(reduce_cost ? "OCF_KSPLIT_FWD" : "OCF_KSPLIT_BWD")) {  // developer override for tuning runs
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4 || v == 8) return v;
+  }
   const long long slots = 2LL * OCF_SM_COUNT;  // 2 resident CTAs per SM
   int best = 1;
   double best_cost = 1e30;
   for (int ks = 1; ks <= 8; ks *= 2) {
     if (ks > 1 && C / ks < min_ch) break;
     const long long rounds = (tiles * ks + slots - 1) / slots;
-    const double cost = (double)rounds / ks + ((ks > 1 && reduce_cost) ? 0.15 : 0.02 * (ks > 1));
+    const double cost = (double)rounds / ks + ((ks > 1 && reduce_cost) ? 0.6 : 0.02 * (ks > 1));
     if (cost < best_cost - 1e-9) { best_cost = cost; best = ks; }
   }
   return best;
@@ -733,7 +748,7 @@ extern "C" int ocf_corr_fwd(const float* f1, const float* f2, float* out, int B,
     if (tma) {
       auto kernel = corr_fwd_tiled<T, STG_TMA>;
       if (int e = set_smem(kernel, smem)) return e;
-      if (int e = launch_kernel(kernel, grid, T::THREADS + 32, smem, s, ks, m1, m2, f1, f2, out, C, H, W, out_bstride, inv_c, leaky_slope, ks)) return e;
+      if (int e = launch_kernel(kernel, grid, T::THREADS, smem, s, ks, m1, m2, f1, f2, out, C, H, W, out_bstride, inv_c, leaky_slope, ks)) return e;
     } else {
       auto kernel = vec ? corr_fwd_tiled<T, STG_ASYNC16> : corr_fwd_tiled<T, STG_ASYNC4>;
       if (int e = set_smem(kernel, smem)) return e;

@@ -104,8 +104,11 @@ warp_fwd_kernel(const float* __restrict__ img, const float* __restrict__ flow, c
 // taps of lane l+1; both coincidences are detected once per pixel (they do not depend on the channel) and the
 // contributions are summed in registers / with one shuffle before the atomic, so a fully coherent neighbourhood
 // issues (R+1)/R atomics per pixel and channel instead of 4.
+// (Measured, profiles/: every lane of a scalar red is its own 32-byte sector-op in the L2 atomic unit; a variant that
+// re-aligned coherent 8-lane segments into red.global.add.v4.f32 cut sector-ops by a third but not the run time -- the
+// kernel is bound by issue slots and load latency, not by the atomic unit -- so the simpler scalar form is kept.)
 template <int R>
-__global__ void __launch_bounds__(WARP_THREADS)
+__global__ void __launch_bounds__(WARP_THREADS, 2)
 warp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ img, const float* __restrict__ flow,
                 const float* __restrict__ occ, float* __restrict__ d_img, float* __restrict__ d_flow,
                 float* __restrict__ d_occ, int C, int H, int W, int slab, int nslabs, int flags, float scale) {
@@ -174,40 +177,60 @@ warp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ img, c
 #pragma unroll
   for (int r = 0; r < R; ++r) { gx[r] = 0.f; gy[r] = 0.f; go[r] = 0.f; }
   const bool need_vals = d_flow != nullptr || d_occ != nullptr;
-#pragma unroll 2
-  for (int c = c_begin; c < c_end; ++c, ip += HW, gp += HW) {
-    float cnw[R], cne[R], csw[R], cse[R];
+  // Channels go in batches of CB: all loads of a batch are issued before its first atomic (atomics are ordering points
+  // for the compiler, so without the explicit batch every channel would expose a full global-load latency).
+  constexpr int CB = 2;
+  for (int c0 = c_begin; c0 < c_end; c0 += CB, ip += (size_t)CB * HW, gp += (size_t)CB * HW) {
+    float gv[CB][R], ta[CB][R], tb[CB][R], tc[CB][R], td[CB][R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const float graw = act[r] ? __ldg(gp + pix[r]) : 0.f;
-      const float g = graw * gmul[r];
-      if (need_vals) {
-        const float a = onw[r] >= 0 ? __ldg(ip + onw[r]) : 0.f, bb = one[r] >= 0 ? __ldg(ip + one[r]) : 0.f;
-        const float cc = osw[r] >= 0 ? __ldg(ip + osw[r]) : 0.f, dd = ose[r] >= 0 ? __ldg(ip + ose[r]) : 0.f;
-        // ATen grid_sampler_2d_backward: gix -= nw*(iy_se-iy) ; += ne*(iy_sw-iy) ; -= sw*(iy-iy_ne) ; += se*(iy-iy_nw)
-        gx[r] += g * ((bb - a) * wy0[r] + (dd - cc) * wy1[r]);
-        gy[r] += g * ((cc - a) * wx0[r] + (dd - bb) * wx1[r]);
-        if (d_occ != nullptr) go[r] += graw * mul[r] * (a * wnw[r] + bb * wne[r] + cc * wsw[r] + dd * wse[r]);
-      }
-      cnw[r] = g * wnw[r]; cne[r] = g * wne[r]; csw[r] = g * wsw[r]; cse[r] = g * wse[r];
-    }
-    if (dp != nullptr) {
-#pragma unroll
-      for (int r = 1; r < R; ++r) {
-        if (mvw[r]) cnw[r] += csw[r - 1];
-        if (mve[r]) cne[r] += cse[r - 1];
-      }
+    for (int j = 0; j < CB; ++j) {
+      const bool cok = c0 + j < c_end;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const float pn = __shfl_up_sync(full, cne[r], 1), ps = __shfl_up_sync(full, cse[r], 1);
-        if (take_n[r]) cnw[r] += pn;
-        if (take_s[r]) csw[r] += ps;
-        if (onw[r] >= 0) atomicAdd(dp + onw[r], cnw[r]);
-        if (one[r] >= 0 && !give_n[r]) atomicAdd(dp + one[r], cne[r]);
-        if (emit_sw[r]) atomicAdd(dp + osw[r], csw[r]);
-        if (emit_se[r] && !give_s[r]) atomicAdd(dp + ose[r], cse[r]);
+        gv[j][r] = (cok && act[r]) ? __ldg(gp + (size_t)j * HW + pix[r]) : 0.f;
+        if (need_vals) {
+          ta[j][r] = (cok && onw[r] >= 0) ? __ldg(ip + (size_t)j * HW + onw[r]) : 0.f;
+          tb[j][r] = (cok && one[r] >= 0) ? __ldg(ip + (size_t)j * HW + one[r]) : 0.f;
+          tc[j][r] = (cok && osw[r] >= 0) ? __ldg(ip + (size_t)j * HW + osw[r]) : 0.f;
+          td[j][r] = (cok && ose[r] >= 0) ? __ldg(ip + (size_t)j * HW + ose[r]) : 0.f;
+        }
       }
-      dp += HW;
+    }
+#pragma unroll
+    for (int j = 0; j < CB; ++j) {
+      if (c0 + j >= c_end) break;  // uniform
+      float cnw[R], cne[R], csw[R], cse[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float graw = gv[j][r];
+        const float g = graw * gmul[r];
+        if (need_vals) {
+          const float a = ta[j][r], bb = tb[j][r], cc = tc[j][r], dd = td[j][r];
+          // ATen grid_sampler_2d_backward: gix -= nw*(iy_se-iy) ; += ne*(iy_sw-iy) ; -= sw*(iy-iy_ne) ; += se*(iy-iy_nw)
+          gx[r] += g * ((bb - a) * wy0[r] + (dd - cc) * wy1[r]);
+          gy[r] += g * ((cc - a) * wx0[r] + (dd - bb) * wx1[r]);
+          if (d_occ != nullptr) go[r] += graw * mul[r] * (a * wnw[r] + bb * wne[r] + cc * wsw[r] + dd * wse[r]);
+        }
+        cnw[r] = g * wnw[r]; cne[r] = g * wne[r]; csw[r] = g * wsw[r]; cse[r] = g * wse[r];
+      }
+      if (dp != nullptr) {
+#pragma unroll
+        for (int r = 1; r < R; ++r) {
+          if (mvw[r]) cnw[r] += csw[r - 1];
+          if (mve[r]) cne[r] += cse[r - 1];
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float pn = __shfl_up_sync(full, cne[r], 1), ps = __shfl_up_sync(full, cse[r], 1);
+          if (take_n[r]) cnw[r] += pn;
+          if (take_s[r]) csw[r] += ps;
+          if (onw[r] >= 0) atomicAdd(dp + onw[r], cnw[r]);
+          if (one[r] >= 0 && !give_n[r]) atomicAdd(dp + one[r], cne[r]);
+          if (emit_sw[r]) atomicAdd(dp + osw[r], csw[r]);
+          if (emit_se[r] && !give_s[r]) atomicAdd(dp + ose[r], cse[r]);
+        }
+        dp += HW;
+      }
     }
   }
   // chain: ATen multiplies by (W-1)/2 resp. W/2, the reference's normalisation by 2/max(W-1,1)
