@@ -375,9 +375,16 @@ def main():
         dist.all_reduce(dte, op=dist.ReduceOp.MAX)
     dte = float(dte)
 
-    if rank != 0:
+    def finish():
+        # every rank leaves together: a rank that tears its communicator down (or exits) while rank 0 is still measuring
+        # the roofline leg leaves rank 0's own teardown waiting on a peer that is gone
         if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
             dist.destroy_process_group()
+
+    if rank != 0:
+        finish()
         return
 
     line = {
@@ -420,8 +427,7 @@ def main():
         line["cpu_baseline"] = {"value": b / cdt, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "%d steps x %d of %d pairs at %dx%d after 1 warm-up (oracle port, torch CPU fp32)" % (nrep, b, B, H, W)}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":

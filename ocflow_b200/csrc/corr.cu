@@ -35,6 +35,35 @@
 
 namespace cg = cooperative_groups;
 
+// persistent forward kernel: registers per thread, channel unroll and resident CTAs per SM (tuning knobs)
+#ifndef OCF_FWD_REGS
+#define OCF_FWD_REGS 168
+#endif
+#ifndef OCF_FWD_UNROLL
+#define OCF_FWD_UNROLL 8
+#endif
+#ifndef OCF_FWD_CTAS_PER_SM
+#define OCF_FWD_CTAS_PER_SM 1
+#endif
+
+#ifdef OCF_TIMELINE
+// developer builds only (tools/timeline.py): per-CTA globaltimer stamps of the persistent kernels
+__device__ unsigned long long ocf_tl[1024 * 16];
+__device__ __forceinline__ unsigned long long ocf_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define OCF_TL(slot) do { if (threadIdx.x == 0 && blockIdx.x < 1024) ocf_tl[blockIdx.x * 16 + (slot)] = ocf_now(); } while (0)
+#define OCF_TL_SM() do { if (threadIdx.x == 0 && blockIdx.x < 1024) { unsigned sm; asm("mov.u32 %0, %smid;" : "=r"(sm)); ocf_tl[blockIdx.x * 16 + 15] = sm; } } while (0)
+extern "C" int ocf_debug_timeline(unsigned long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, ocf_tl, sizeof(unsigned long long) * n);
+}
+#else
+#define OCF_TL(slot) do { } while (0)
+#define OCF_TL_SM() do { } while (0)
+#endif
+
 namespace {
 
 constexpr int pad4mod8(int n) {
@@ -106,6 +135,20 @@ __device__ __forceinline__ void tma_load_4d(float* smem_dst, const CUtensorMap* 
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(c), "r"(b)
       : "memory");
 }
+// ---- packed fp32 FMA (Blackwell FFMA2): two IEEE fp32 fused multiply-adds per issue slot ------------
+typedef unsigned long long u64;
+template <int V>
+struct IntC {
+  static constexpr int value = V;
+};
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void ffma2(u64& d, u64 a, u64 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); }
+
 template <int THREADS>
 __device__ __forceinline__ void consumer_bar_sync() {  // named barrier 1: the compute warps only (the producer warp is not part)
   asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
@@ -169,7 +212,7 @@ __device__ __forceinline__ ChunkRange chunk_range(int C, int CC, int ksplit, int
 // ---- forward ------------------------------------------------------------------------------------
 // grid (tiles_x, tiles_y, B * ksplit); when ksplit > 1 the launch carries cluster dims (1, 1, ksplit).
 template <class T, int STG>
-__global__ void __launch_bounds__(T::THREADS, 2)
+__global__ void __maxnreg__(96)
 corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2, const float* __restrict__ f1,
                const float* __restrict__ f2, float* __restrict__ out, int C, int H, int W, long long out_bstride, float inv_c,
                float slope, int ksplit) {
@@ -189,18 +232,28 @@ corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
   const ChunkRange cr = chunk_range(C, CC, ksplit, ks);
   const int nchunks = cr.count;
 
-  float acc[ND][PX];
+  // Accumulators.  out[dx][p] += a[p] * w[p + dx]: for a fixed pixel p the 2d+1 products share a[p] and walk consecutive
+  // window elements, so they are issued as packed FFMA2 (scalar a[p] broadcast x aligned pair of w): pixel p pairs the
+  // displacements (dx, dx+1) with p + dx even -- dx = 0,2,.. for even p, dx = 1,3,.. for odd p -- and keeps the one
+  // left-over displacement (dx = 2d for even p, dx = 0 for odd p) in a scalar FFMA.  Per channel: D*PX FFMA2 + PX FFMA
+  // instead of (2D+1)*PX FFMA; same IEEE results, same summation order.
+  static_assert(PX % 2 == 0, "pixel pairs");
+  u64 accp[PX][D];
+  float accs[PX];
 #pragma unroll
-  for (int i = 0; i < ND; ++i)
+  for (int p = 0; p < PX; ++p) {
+    accs[p] = 0.f;
 #pragma unroll
-    for (int p = 0; p < PX; ++p) acc[i][p] = 0.f;
+    for (int j = 0; j < D; ++j) accp[p][j] = 0ull;
+  }
 
   auto compute = [&](const float* st) {
     const float* p1 = st + ty * S1 + tx * PX;
     const float* p2 = st + T::F1_STAGE + (ty + dyi) * S2 + tx * PX;
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < CC; ++c) {
-      float a[PX], w[WIN];
+      float a[PX];
+      u64 w2[WIN / 2];
 #pragma unroll
       for (int q = 0; q < PX / 4; ++q) {
         const float4 v = *reinterpret_cast<const float4*>(p1 + c * TH * S1 + 4 * q);
@@ -208,14 +261,34 @@ corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
       }
 #pragma unroll
       for (int q = 0; q < WIN / 4; ++q) {
-        const float4 v = *reinterpret_cast<const float4*>(p2 + c * F2H * S2 + 4 * q);
-        w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p2 + c * F2H * S2 + 4 * q);
+        w2[2 * q] = v.x; w2[2 * q + 1] = v.y;
       }
 #pragma unroll
-      for (int dx = 0; dx < ND; ++dx)
+      for (int p = 0; p < PX; ++p) {
+        const u64 ap = pack2(a[p], a[p]);
+        const int first = p & 1;  // first paired displacement
 #pragma unroll
-        for (int p = 0; p < PX; ++p) acc[dx][p] = fmaf(a[p], w[p + dx], acc[dx][p]);
+        for (int j = 0; j < D; ++j) ffma2(accp[p][j], ap, w2[(p + first + 2 * j) / 2]);
+        float lo, hi;
+        if (first == 0) {  // left-over dx = 2D: w[p + 2D]
+          unpack2(w2[(p + 2 * D) / 2], lo, hi);
+          accs[p] = fmaf(a[p], lo, accs[p]);
+        } else {           // left-over dx = 0: w[p]
+          unpack2(w2[p / 2], lo, hi);
+          accs[p] = fmaf(a[p], hi, accs[p]);
+        }
+      }
     }
+  };
+  // unpacked view for the epilogue
+  auto acc_get = [&](int dx, int p) -> float {
+    const int first = p & 1;
+    if (first == 0 && dx == 2 * D) return accs[p];
+    if (first == 1 && dx == 0) return accs[p];
+    float lo, hi;
+    unpack2(accp[p][(dx - first) / 2], lo, hi);
+    return ((dx - first) & 1) ? hi : lo;
   };
 
   if constexpr (TMA) {
@@ -240,14 +313,15 @@ corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
     __syncthreads();
     for (int i = 0; i < nchunks; ++i) {
       const int s = i % STAGES;
+      // refill the stage released one iteration ago (deferred so that thread 0 does not wait for the slowest warp)
+      if (tid == 0 && i >= 1 && i - 1 + STAGES < nchunks) {
+        mbar_wait(&empty_bar[(i - 1) % STAGES], ((i - 1) / STAGES) & 1);
+        issue_tma(i - 1 + STAGES);
+      }
       mbar_wait(&full_bar[s], (i / STAGES) & 1);
       compute(smem + s * STAGE);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);
-      if (tid == 0 && i + STAGES < nchunks) {  // refill this stage as soon as all 9 warps have released it
-        mbar_wait(&empty_bar[s], (i / STAGES) & 1);
-        issue_tma(i + STAGES);
-      }
     }
   } else {
     const float* f1b = f1 + (size_t)b * C * H * W;
@@ -284,7 +358,7 @@ corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
       float r[PX];
 #pragma unroll
       for (int p = 0; p < PX; ++p) {
-        const float v = acc[dx][p] * inv_c;
+        const float v = acc_get(dx, p) * inv_c;
         r[p] = v > 0.f ? v : v * slope;
       }
       float* o = ob + (size_t)dx * H * W;
@@ -312,7 +386,7 @@ corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
       float* pp = part + ((dyi * ND + dx) * TH + ty) * S1 + tx * PX;
 #pragma unroll
       for (int q = 0; q < PX / 4; ++q)
-        *reinterpret_cast<float4*>(pp + 4 * q) = make_float4(acc[dx][4 * q], acc[dx][4 * q + 1], acc[dx][4 * q + 2], acc[dx][4 * q + 3]);
+        *reinterpret_cast<float4*>(pp + 4 * q) = make_float4(acc_get(dx, 4 * q), acc_get(dx, 4 * q + 1), acc_get(dx, 4 * q + 2), acc_get(dx, 4 * q + 3));
     }
   }
   cluster.sync();
@@ -353,6 +427,159 @@ corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
     }
   }
   cluster.sync();  // nobody may exit while a peer still reads its shared memory
+}
+
+// ---- forward, persistent (regular shapes, no channel split) -----------------------------------------
+// One CTA per resident slot (2 per SM) walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The TMA ring keeps
+// running ACROSS tile boundaries: while the warps finish tile t and store its 81 planes, the boxes of tile t+1 are
+// already in flight, so only the first tile of a CTA pays the cold-start latency (at C = 32 a tile is just 4 chunks --
+// without this every tile would wait ~1.5 us for its first box with nothing else to do).
+template <class T, int UNROLL>
+__global__ void __maxnreg__(OCF_FWD_REGS)
+corr_fwd_persist(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2, float* __restrict__ out, int C,
+                 int H, int W, long long out_bstride, float inv_c, float slope, int tiles_x, int tiles_y, int ntiles) {
+  constexpr int D = T::D, PX = T::PX, ND = T::ND, TH = T::TH, TW = T::TW, CC = T::CC, STAGES = T::STAGES;
+  constexpr int S1 = T::S1, S2 = T::S2, F2H = T::F2H, WIN = T::WIN;
+  constexpr int STAGE = T::F1_STAGE + T::F2_STAGE;
+  constexpr unsigned BYTES = sizeof(float) * STAGE;
+  static_assert(PX % 2 == 0, "pixel pairs");
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES];
+
+  const int tid = threadIdx.x;
+  const int lane = tid % T::LANES;
+  const int tx = lane % T::TXT, ty = lane / T::TXT;
+  const int dyi = tid / T::LANES;
+  OCF_TL(0);
+  OCF_TL_SM();
+  const int nchunks = (C + CC - 1) / CC;
+  const int ntl = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int total = ntl * nchunks;
+  const size_t bstride = out_bstride ? (size_t)out_bstride : (size_t)ND * ND * H * W;
+
+  // producer state (thread 0 only): next flat chunk to issue = (tile iteration pk, chunk pi)
+  int pk = 0, pi = 0, pn = 0;
+  auto issue_next = [&]() {
+    const int tile = (int)blockIdx.x + pk * (int)gridDim.x;
+    const int txi = tile % tiles_x, r = tile / tiles_x;
+    const int tyi = r % tiles_y, b = r / tiles_y;
+    const int s = pn % STAGES;
+    float* st = smem + s * STAGE;
+    mbar_expect_tx(&full_bar[s], BYTES);
+    tma_load_4d(st, &map1, &full_bar[s], txi * TW, tyi * TH, pi * CC, b);
+    tma_load_4d(st + T::F1_STAGE, &map2, &full_bar[s], txi * TW - D, tyi * TH - D, pi * CC, b);
+    ++pn;
+    if (++pi == nchunks) { pi = 0; ++pk; }
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ND); }
+    mbar_fence_init();
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s)
+      if (pn < total) issue_next();
+  }
+  __syncthreads();
+
+  u64 accp[PX][D];
+  float accs[PX];
+#pragma unroll
+  for (int p = 0; p < PX; ++p) {
+    accs[p] = 0.f;
+#pragma unroll
+    for (int j = 0; j < D; ++j) accp[p][j] = 0ull;
+  }
+  const int o1 = ty * S1 + tx * PX;
+  const int o2 = T::F1_STAGE + (ty + dyi) * S2 + tx * PX;
+
+  int n = 0;  // flat chunk counter of this CTA
+  for (int k = 0; k < ntl; ++k) {
+    for (int i = 0; i < nchunks; ++i, ++n) {
+      const int s = n % STAGES;
+      // refill the stage released one step ago (deferred so that thread 0 does not wait for the slowest warp)
+      if (tid == 0 && n >= 1 && pn < total) {
+        mbar_wait(&empty_bar[(n - 1) % STAGES], ((n - 1) / STAGES) & 1);
+        issue_next();
+      }
+      mbar_wait(&full_bar[s], (n / STAGES) & 1);
+      if (n == 0) OCF_TL(1);
+      const float* st = smem + s * STAGE;
+      const float* p1 = st + o1;
+      const float* p2 = st + o2;
+#pragma unroll UNROLL
+      for (int c = 0; c < CC; ++c) {
+        float a[PX];
+        u64 w2[WIN / 2];
+#pragma unroll
+        for (int q = 0; q < PX / 4; ++q) {
+          const float4 v = *reinterpret_cast<const float4*>(p1 + c * TH * S1 + 4 * q);
+          a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int q = 0; q < WIN / 4; ++q) {
+          const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p2 + c * F2H * S2 + 4 * q);
+          w2[2 * q] = v.x; w2[2 * q + 1] = v.y;
+        }
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+          const u64 ap = pack2(a[p], a[p]);
+          const int first = p & 1;
+#pragma unroll
+          for (int j = 0; j < D; ++j) ffma2(accp[p][j], ap, w2[(p + first + 2 * j) / 2]);
+          float lo, hi;
+          if (first == 0) {
+            unpack2(w2[(p + 2 * D) / 2], lo, hi);
+            accs[p] = fmaf(a[p], lo, accs[p]);
+          } else {
+            unpack2(w2[p / 2], lo, hi);
+            accs[p] = fmaf(a[p], hi, accs[p]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+    // ---- epilogue of tile k: 1/C, LeakyReLU, 128-bit stores; accumulators restart from zero ----
+    if (k < 3) OCF_TL(2 + 2 * k);
+    const int tile = (int)blockIdx.x + k * (int)gridDim.x;
+    const int txi = tile % tiles_x, r = tile / tiles_x;
+    const int tyi = r % tiles_y, b = r / tiles_y;
+    const int y = tyi * TH + ty, xs = txi * TW + tx * PX;
+    const bool inside = y < H && xs < W;
+    float* ob = out + (size_t)b * bstride + ((size_t)(dyi * ND) * H + y) * W + xs;
+#pragma unroll
+    for (int dx = 0; dx < ND; ++dx) {
+      float rr[PX];
+#pragma unroll
+      for (int p = 0; p < PX; ++p) {
+        const int first = p & 1;
+        float v;
+        if ((first == 0 && dx == 2 * D) || (first == 1 && dx == 0)) {
+          v = accs[p];
+        } else {
+          float lo, hi;
+          unpack2(accp[p][(dx - first) / 2], lo, hi);
+          v = ((dx - first) & 1) ? hi : lo;
+        }
+        v *= inv_c;
+        rr[p] = v > 0.f ? v : v * slope;
+      }
+      if (inside) {
+        float* o = ob + (size_t)dx * H * W;
+#pragma unroll
+        for (int q = 0; q < PX / 4; ++q)
+          if (xs + 4 * q < W) *reinterpret_cast<float4*>(o + 4 * q) = make_float4(rr[4 * q], rr[4 * q + 1], rr[4 * q + 2], rr[4 * q + 3]);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      accs[p] = 0.f;
+#pragma unroll
+      for (int j = 0; j < D; ++j) accp[p][j] = 0ull;
+    }
+    if (k < 3) OCF_TL(3 + 2 * k);
+  }
+  OCF_TL(14);
 }
 
 // Any displacement up to OCF_MAX_DISPLACEMENT: one thread per (pixel, dy), operands through L1/L2.
@@ -396,10 +623,15 @@ corr_fwd_generic(const float* __restrict__ f1, const float* __restrict__ f2, flo
 // ---- backward -----------------------------------------------------------------------------------
 // mode 0: dout = d f1, fo = f2 ; mode 1: dout = d f2, fo = f1.
 // blockIdx.z = (b * nmodes + slot) * ksplit + channel slice.
+//
+// Per thread: part[p] = sum_dx G[dx][p] * w[p + dx] for its PX pixels and its dy.  Issued as packed FFMA2 with two
+// accumulator sets: even dx pairs the pixels (0,1)(2,3).. with the window pairs (p+dx, p+dx+1), odd dx pairs (1,2)(3,4)..
+// (again p + dx even, i.e. an aligned register pair of the window) and keeps pixels 0 and PX-1 in scalar FFMAs.  The 81
+// coefficients live in registers for the whole kernel, already laid out as those pairs; they are fetched with 128-bit
+// global loads straight into registers WHILE the first feature chunks are in flight (no staging pass, no extra shared memory).
 template <class T, int CR, int STG>
-__global__ void __launch_bounds__(Threads<T, STG>::value, 2)
-corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
-               const __grid_constant__ CUtensorMap mapg, const __grid_constant__ CUtensorMap mapa, const float* __restrict__ g,
+__global__ void __maxnreg__(96)
+corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2, const float* __restrict__ g,
                const float* __restrict__ oact, const float* __restrict__ f1, const float* __restrict__ f2, float* __restrict__ df1,
                float* __restrict__ df2, int C, int H, int W, long long g_bstride, float inv_c, float slope, int nmodes,
                int first_mode, int ksplit) {
@@ -407,18 +639,18 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
   constexpr int S1 = T::S1, S2 = T::S2, F2H = T::F2H, F2W = T::F2W, WIN = T::WIN;
   constexpr bool TMA = STG == STG_TMA;
   constexpr bool VEC = STG != STG_ASYNC4;
+  constexpr int NE = D + 1, NO = D;        // number of even / odd horizontal displacements
+  constexpr int PE = PX / 2, PO = PX / 2 - 1;  // pixel pairs per even / odd displacement
   static_assert(CC % CR == 0, "CC must be a multiple of CR");
+  static_assert(PX == 8 && D % 2 == 0, "pair layout below assumes 8 pixels per thread and an even displacement radius");
   extern __shared__ __align__(128) float smem[];
-  __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES], g_bar, gdone_bar;
+  __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES];
   float* red = smem + STAGES * T::F2_STAGE;  // [ND][CR][TH][S1]
-  // TMA variant: the 81 coefficient planes of the tile are staged through shared memory first (one {GW, TH, ND} box per
-  // dy-warp, GW == 12 mod 32 floats so the 128-bit reads are conflict-free); the area is then reused by the ring + red.
-  constexpr int GW = T::S2, BOXG = ND * TH * GW;
 
   const int tid = threadIdx.x;
   const int lane = tid % T::LANES;
   const int tx = lane % T::TXT, ty = lane / T::TXT;
-  const int dyi = tid / T::LANES;  // == ND for the TMA producer warp
+  const int dyi = tid / T::LANES;
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
   const int zz = blockIdx.z / ksplit, ks = blockIdx.z - zz * ksplit;
   const int b = zz / nmodes;
@@ -427,116 +659,115 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
   const int nchunks = cr.count;
   float* dout = (mode == 0 ? df1 : df2) + (size_t)b * C * H * W;
   const size_t gb = (g_bstride ? (size_t)g_bstride : (size_t)ND * ND * H * W) * b;
-
-  float G[ND][PX];  // 81 per-pixel coefficients of this thread's dy row, kept in registers for the whole kernel
-  if constexpr (TMA) {
-    if (tid == 0) {
-#pragma unroll
-      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ND); }
-      mbar_init(&g_bar, 1);
-      mbar_init(&gdone_bar, ND);
-      mbar_fence_init();
-    }
-    __syncthreads();
-    const bool has_act = oact != nullptr;
-    if (dyi == ND) {
-      if (lane == 0) {
-        // coefficient boxes: mode 0 -> planes dy*ND.. at (y0, x0) ; mode 1 -> planes (2D-dy)*ND.. at (y0+dy-D, x0-D)
-        constexpr unsigned GBYTES = sizeof(float) * ND * BOXG;
-        for (int pass = 0; pass < (has_act ? 2 : 1); ++pass) {
-          if (pass == 1) mbar_wait(&gdone_bar, 0);  // every warp has lifted its coefficients out of the staging area
-          mbar_expect_tx(&g_bar, GBYTES);
-          for (int w = 0; w < ND; ++w) {
-            const int plane0 = mode == 0 ? w * ND : (2 * D - w) * ND;
-            tma_load_4d(smem + w * BOXG, pass == 0 ? &mapg : &mapa, &g_bar, mode == 0 ? x0 : x0 - D, mode == 0 ? y0 : y0 + w - D, plane0, b);
-          }
-        }
-        mbar_wait(&gdone_bar, has_act ? 1 : 0);  // staging area is free: start feeding the feature ring
-        constexpr unsigned BYTES = sizeof(float) * T::F2_STAGE;
-        const CUtensorMap* map = mode == 0 ? &map2 : &map1;  // the OTHER feature
-        for (int i = 0; i < nchunks; ++i) {
-          const int s = i % STAGES;
-          if (i >= STAGES) mbar_wait(&empty_bar[s], ((i / STAGES) - 1) & 1);
-          mbar_expect_tx(&full_bar[s], BYTES);
-          tma_load_4d(smem + s * T::F2_STAGE, map, &full_bar[s], x0 - D, y0 - D, (cr.begin + i) * CC, b);
-        }
-      }
-      return;  // the producer warp takes no part in the compute-warp barriers below
-    }
-    const float* gw = smem + dyi * BOXG + ty * GW + tx * PX;
-    for (int pass = 0; pass < (has_act ? 2 : 1); ++pass) {
-      mbar_wait(&g_bar, pass);
-      if (mode == 0) {
-#pragma unroll
-        for (int dx = 0; dx < ND; ++dx) {
-          float t[PX];
-#pragma unroll
-          for (int q = 0; q < PX / 4; ++q) {
-            const float4 v = *reinterpret_cast<const float4*>(gw + dx * TH * GW + 4 * q);
-            t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
-          }
-#pragma unroll
-          for (int p = 0; p < PX; ++p) {
-            if (pass == 0) G[dx][p] = t[p];
-            else if (!(t[p] > 0.f)) G[dx][p] *= slope;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int dx = 0; dx < ND; ++dx) {
-          float t[PX + 4];
-#pragma unroll
-          for (int q = 0; q < PX / 4 + 1; ++q) {
-            const float4 v = *reinterpret_cast<const float4*>(gw + (2 * D - dx) * TH * GW + (dx & ~3) + 4 * q);
-            t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
-          }
-#pragma unroll
-          for (int p = 0; p < PX; ++p) {
-            const float v = t[p + (dx & 3)];
-            if (pass == 0) G[dx][p] = v;
-            else if (!(v > 0.f)) G[dx][p] *= slope;
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&gdone_bar);
-    }
-  }
   const float* fo = (mode == 0 ? f2 : f1) + (size_t)b * C * H * W;
+
+  // ---- start the feature ring first: its latency overlaps the coefficient loads below ----
+  constexpr unsigned BYTES = sizeof(float) * T::F2_STAGE;
+  auto issue_tma = [&](int i) {
+    const int s = i % STAGES;
+    const CUtensorMap* map = mode == 0 ? &map2 : &map1;  // the OTHER feature
+    mbar_expect_tx(&full_bar[s], BYTES);
+    tma_load_4d(smem + s * T::F2_STAGE, map, &full_bar[s], x0 - D, y0 - D, (cr.begin + i) * CC, b);
+  };
   auto issue = [&](int i) {
     stage_box_async<CC, F2H, F2W, S2, T::THREADS, STG == STG_ASYNC16>(smem + (i % STAGES) * T::F2_STAGE, fo, (cr.begin + i) * CC, C, H, W,
                                                                       y0 - D, x0 - D);
   };
-  if constexpr (!TMA) {
+  if constexpr (TMA) {
+    if (tid == 0) {
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ND); }
+      mbar_fence_init();
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s)
+        if (s < nchunks) issue_tma(s);
+    }
+  } else {
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
       if (s < nchunks) issue(s);
       cp_async_commit();
     }
+  }
+
+  // ---- the 81 coefficients of this thread's dy row (LeakyReLU mask of the forward folded in) ----
+  // mode 0: G[dx][p] = g[k(dy,dx)][y][xs+p] ; mode 1: G[dx][p] = g[k(-dy,-dx)][y+dy][xs+p+dx]
+  float G[ND][PX];
+  auto load_coefficients = [&](auto mode_c) {
+    constexpr int mode = decltype(mode_c)::value;
     const int y = y0 + ty, xs = x0 + tx * PX;
 #pragma unroll
     for (int dx = 0; dx < ND; ++dx) {
-      // mode 0: plane k(dy,dx) at (y, x) ; mode 1: plane k(-dy,-dx) at (y+dy, x+dx)
       const int k = mode == 0 ? dyi * ND + dx : (2 * D - dyi) * ND + (2 * D - dx);
       const int sy = mode == 0 ? y : y + dyi - D;
-      const int sx0 = mode == 0 ? xs : xs + dx - D;
       const size_t off = gb + ((size_t)k * H + sy) * W;
+      const bool rowok = sy >= 0 && sy < H;
+      if (VEC) {
+        // aligned 128-bit loads; W % 4 == 0 so every float4 is entirely inside or outside the row
+        constexpr int NV = PX / 4 + 1;
+        const int sh = mode == 0 ? 0 : dx - D;        // horizontal shift of the coefficient row
+        const int base = xs + (sh & ~3);                  // floor to a multiple of 4 (two's complement: also for negatives)
+        const int o = sh & 3;
+        float t[4 * NV];
 #pragma unroll
-      for (int p = 0; p < PX; ++p) {
-        const int sx = sx0 + p;
-        float v = 0.f;
-        if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
-          v = __ldg(g + off + sx);
-          if (oact != nullptr && !(__ldg(oact + off + sx) > 0.f)) v *= slope;
+        for (int q = 0; q < NV; ++q) {
+          const int gx = base + 4 * q;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rowok && gx >= 0 && gx < W && (q < NV - 1 || o != 0)) {
+            v = __ldg(reinterpret_cast<const float4*>(g + off + gx));
+            if (oact != nullptr) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(oact + off + gx));
+              if (!(a.x > 0.f)) v.x *= slope;
+              if (!(a.y > 0.f)) v.y *= slope;
+              if (!(a.z > 0.f)) v.z *= slope;
+              if (!(a.w > 0.f)) v.w *= slope;
+            }
+          }
+          t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
         }
-        G[dx][p] = v;
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+          G[dx][p] = t[p + o];
+        }
+      } else {
+        const int sx0 = mode == 0 ? xs : xs + dx - D;
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+          const int sx = sx0 + p;
+          float v = 0.f;
+          if (rowok && sx >= 0 && sx < W) {
+            v = __ldg(g + off + sx);
+            if (oact != nullptr && !(__ldg(oact + off + sx) > 0.f)) v *= slope;
+          }
+          G[dx][p] = v;
+        }
       }
     }
+  };
+  if (mode == 0) load_coefficients(IntC<0>{}); else load_coefficients(IntC<1>{});
+  // pair layout for FFMA2
+  u64 GE[NE][PE], GO[NO][PO];
+  float G0[NO], G7[NO];
+#pragma unroll
+  for (int e = 0; e < NE; ++e)
+#pragma unroll
+    for (int j = 0; j < PE; ++j) GE[e][j] = pack2(G[2 * e][2 * j], G[2 * e][2 * j + 1]);
+#pragma unroll
+  for (int o = 0; o < NO; ++o) {
+#pragma unroll
+    for (int j = 0; j < PO; ++j) GO[o][j] = pack2(G[2 * o + 1][2 * j + 1], G[2 * o + 1][2 * j + 2]);
+    G0[o] = G[2 * o + 1][0];
+    G7[o] = G[2 * o + 1][PX - 1];
   }
+  if constexpr (TMA) __syncthreads();  // barrier initialisation visible to every thread before the first wait
 
   for (int i = 0; i < nchunks; ++i) {
     const int s = i % STAGES;
     if constexpr (TMA) {
+      if (tid == 0 && i >= 1 && i - 1 + STAGES < nchunks) {  // deferred refill of the stage released one iteration ago
+        mbar_wait(&empty_bar[(i - 1) % STAGES], ((i - 1) / STAGES) & 1);
+        issue_tma(i - 1 + STAGES);
+      }
       mbar_wait(&full_bar[s], (i / STAGES) & 1);
     } else {
       cp_async_wait<STAGES - 2>();
@@ -551,24 +782,53 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
       if (c0 + r0 >= C) break;  // uniform across the block
 #pragma unroll
       for (int c = 0; c < CR; ++c) {
-        float w[WIN], part[PX];
+        u64 w2[WIN / 2];
 #pragma unroll
         for (int q = 0; q < WIN / 4; ++q) {
-          const float4 v = *reinterpret_cast<const float4*>(pw + (r0 + c) * F2H * S2 + 4 * q);
-          w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+          const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(pw + (r0 + c) * F2H * S2 + 4 * q);
+          w2[2 * q] = v.x; w2[2 * q + 1] = v.y;
         }
+        u64 pe[PE], po[PO];
+        float s0 = 0.f, s7 = 0.f;
 #pragma unroll
-        for (int p = 0; p < PX; ++p) part[p] = 0.f;
+        for (int j = 0; j < PE; ++j) pe[j] = 0ull;
 #pragma unroll
-        for (int dx = 0; dx < ND; ++dx)
+        for (int j = 0; j < PO; ++j) po[j] = 0ull;
 #pragma unroll
-          for (int p = 0; p < PX; ++p) part[p] = fmaf(G[dx][p], w[p + dx], part[p]);
+        for (int e = 0; e < NE; ++e)  // dx = 2e: pixels (2j, 2j+1) x window (2j+2e, 2j+2e+1)
+#pragma unroll
+          for (int j = 0; j < PE; ++j) ffma2(pe[j], GE[e][j], w2[j + e]);
+#pragma unroll
+        for (int o = 0; o < NO; ++o) {  // dx = 2o+1: pixels (2j+1, 2j+2) x window (2j+2o+2, 2j+2o+3)
+#pragma unroll
+          for (int j = 0; j < PO; ++j) ffma2(po[j], GO[o][j], w2[j + o + 1]);
+          float lo, hi;
+          unpack2(w2[o], lo, hi);                 // pixel 0: window element 2o+1
+          s0 = fmaf(G0[o], hi, s0);
+          unpack2(w2[(PX + 2 * o) / 2], lo, hi);  // pixel PX-1: window element PX-1 + 2o+1 = PX + 2o
+          s7 = fmaf(G7[o], lo, s7);
+        }
+        float part[PX];
+        {
+          float elo[PE], ehi[PE], olo[PO], ohi[PO];
+#pragma unroll
+          for (int j = 0; j < PE; ++j) unpack2(pe[j], elo[j], ehi[j]);
+#pragma unroll
+          for (int j = 0; j < PO; ++j) unpack2(po[j], olo[j], ohi[j]);
+          part[0] = elo[0] + s0;
+          part[PX - 1] = ehi[PE - 1] + s7;
+#pragma unroll
+          for (int j = 0; j < PO; ++j) {
+            part[2 * j + 1] = ehi[j] + olo[j];
+            part[2 * j + 2] = elo[j + 1] + ohi[j];
+          }
+        }
         float* rp = red + ((dyi * CR + c) * TH + ty) * S1 + tx * PX;
 #pragma unroll
         for (int q = 0; q < PX / 4; ++q)
           *reinterpret_cast<float4*>(rp + 4 * q) = make_float4(part[4 * q], part[4 * q + 1], part[4 * q + 2], part[4 * q + 3]);
       }
-      if constexpr (TMA) consumer_bar_sync<T::THREADS>(); else __syncthreads();
+      __syncthreads();
       // cross-dy reduction: CR*TH*TW/4 float4 outputs
       constexpr int OUT4 = CR * TH * TW / 4;
       for (int j = tid; j < OUT4; j += T::THREADS) {
@@ -593,10 +853,10 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
           }
         }
       }
-      if constexpr (TMA) consumer_bar_sync<T::THREADS>(); else __syncthreads();
+      __syncthreads();
     }
     if constexpr (TMA) {
-      // the last consumer barrier above ordered every warp's reads of this stage: one arrival per warp frees it
+      // the last barrier above ordered every warp's reads of this stage: one arrival per warp frees it
       if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
   }
@@ -644,7 +904,12 @@ corr_bwd_generic(const float* __restrict__ g, const float* __restrict__ oact, co
 }
 
 using Tile4 = CorrTile<4, 8, 4, 8, 8, 3>;
+#ifndef OCF_FWD_STAGES
+#define OCF_FWD_STAGES 6
+#endif
+using Tile4P = CorrTile<4, 8, 4, 8, 8, OCF_FWD_STAGES>;  // persistent forward: one CTA per SM, deep ring
 constexpr int BWD_CR = 4;
+constexpr int FWD_UNROLL = OCF_FWD_UNROLL;
 
 template <class K>
 int set_smem(K kernel, size_t bytes) {
@@ -745,7 +1010,15 @@ extern "C" int ocf_corr_fwd(const float* f1, const float* f2, float* out, int B,
     memset(&m1, 0, sizeof(m1));
     memset(&m2, 0, sizeof(m2));
     const bool tma = vec && make_map(&m1, f1, B, C, H, W, T::S1, T::TH, T::CC) && make_map(&m2, f2, B, C, H, W, T::S2, T::F2H, T::CC);
-    if (tma) {
+    if (tma && ks == 1) {
+      using TP = Tile4P;
+      auto kernel = corr_fwd_persist<TP, FWD_UNROLL>;
+      const size_t psmem = sizeof(float) * TP::STAGES * (TP::F1_STAGE + TP::F2_STAGE);
+      if (int e = set_smem(kernel, psmem)) return e;
+      const int ntiles = gx * gy * B;
+      const int nblk = ntiles < OCF_FWD_CTAS_PER_SM * OCF_SM_COUNT ? ntiles : OCF_FWD_CTAS_PER_SM * OCF_SM_COUNT;
+      if (int e = launch_kernel(kernel, dim3(nblk), TP::THREADS, psmem, s, 1, m1, m2, out, C, H, W, out_bstride, inv_c, leaky_slope, gx, gy, ntiles)) return e;
+    } else if (tma) {
       auto kernel = corr_fwd_tiled<T, STG_TMA>;
       if (int e = set_smem(kernel, smem)) return e;
       if (int e = launch_kernel(kernel, grid, T::THREADS, smem, s, ks, m1, m2, f1, f2, out, C, H, W, out_bstride, inv_c, leaky_slope, ks)) return e;
@@ -775,7 +1048,7 @@ extern "C" int ocf_corr_bwd(const float* grad_out, const float* out_act, const f
   const float inv_c = 1.0f / (float)C;
   if (d == 4) {
     using T = Tile4;
-    size_t smem = sizeof(float) * (T::STAGES * T::F2_STAGE + T::ND * BWD_CR * T::TH * T::S1);
+    const size_t smem = sizeof(float) * (T::STAGES * T::F2_STAGE + T::ND * BWD_CR * T::TH * T::S1);
     const int nmodes = (df1 != nullptr && df2 != nullptr) ? 2 : 1;
     const int first = df1 != nullptr ? 0 : 1;
     const int gx = (W + T::TW - 1) / T::TW, gy = (H + T::TH - 1) / T::TH;
@@ -783,27 +1056,21 @@ extern "C" int ocf_corr_bwd(const float* grad_out, const float* out_act, const f
     dim3 grid(gx, gy, B * nmodes * ks);
     const bool vec = (W % 4 == 0) && ocf_aligned16(f1) && ocf_aligned16(f2) && (df1 == nullptr || ocf_aligned16(df1)) &&
                      (df2 == nullptr || ocf_aligned16(df2));
-    CUtensorMap m1, m2, mg, ma;
+    CUtensorMap m1, m2;
     memset(&m1, 0, sizeof(m1));
     memset(&m2, 0, sizeof(m2));
-    memset(&mg, 0, sizeof(mg));
-    memset(&ma, 0, sizeof(ma));
     const long long gbs = g_bstride ? g_bstride : nd * nd * H * W;
-    bool tma = vec && ocf_aligned16(grad_out) && (out_act == nullptr || ocf_aligned16(out_act)) && (gbs % 4 == 0);
-    tma = tma && make_map(&m1, f1, B, C, H, W, T::S2, T::F2H, T::CC) && make_map(&m2, f2, B, C, H, W, T::S2, T::F2H, T::CC) &&
-          make_map(&mg, grad_out, B, (int)(nd * nd), H, W, T::S2, T::TH, T::ND, gbs) &&
-          (out_act == nullptr || make_map(&ma, out_act, B, (int)(nd * nd), H, W, T::S2, T::TH, T::ND, gbs));
+    const bool gvec = ocf_aligned16(grad_out) && (out_act == nullptr || ocf_aligned16(out_act)) && (gbs % 4 == 0);
+    const bool tma = vec && gvec && make_map(&m1, f1, B, C, H, W, T::S2, T::F2H, T::CC) && make_map(&m2, f2, B, C, H, W, T::S2, T::F2H, T::CC);
     if (tma) {
-      const size_t gstage = sizeof(float) * T::ND * T::ND * T::TH * T::S2;  // coefficient staging, reused by ring + red
-      if (gstage > smem) smem = gstage;
       auto kernel = corr_bwd_tiled<T, BWD_CR, STG_TMA>;
       if (int e = set_smem(kernel, smem)) return e;
-      if (int e = launch_kernel(kernel, grid, T::THREADS + 32, smem, s, 1, m1, m2, mg, ma, grad_out, out_act, f1, f2, df1, df2, C, H, W, g_bstride,
+      if (int e = launch_kernel(kernel, grid, T::THREADS, smem, s, 1, m1, m2, grad_out, out_act, f1, f2, df1, df2, C, H, W, g_bstride,
                                 inv_c, leaky_slope, nmodes, first, ks)) return e;
     } else {
-      auto kernel = vec ? corr_bwd_tiled<T, BWD_CR, STG_ASYNC16> : corr_bwd_tiled<T, BWD_CR, STG_ASYNC4>;
+      auto kernel = (vec && gvec) ? corr_bwd_tiled<T, BWD_CR, STG_ASYNC16> : corr_bwd_tiled<T, BWD_CR, STG_ASYNC4>;
       if (int e = set_smem(kernel, smem)) return e;
-      if (int e = launch_kernel(kernel, grid, T::THREADS, smem, s, 1, m1, m2, mg, ma, grad_out, out_act, f1, f2, df1, df2, C, H, W, g_bstride,
+      if (int e = launch_kernel(kernel, grid, T::THREADS, smem, s, 1, m1, m2, grad_out, out_act, f1, f2, df1, df2, C, H, W, g_bstride,
                                 inv_c, leaky_slope, nmodes, first, ks)) return e;
     }
   } else {
