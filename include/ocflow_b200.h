@@ -62,11 +62,13 @@ int ocf_corr_fwd(const float* f1, const float* f2, float* out, int B, int C, int
  *   df1[b,c,y,x] = (1/C) sum_k g'[b,k,y,x] * f2[b,c,y+dy,x+dx]
  *   df2[b,c,y,x] = (1/C) sum_k g'[b,k,y-dy,x-dx] * f1[b,c,y-dy,x-dx]
  *   g' = grad_out, or grad_out * LeakyReLU'(out_act) when out_act != NULL (out_act = the activated
- *   forward output, same strides as grad_out).  df1 or df2 may be NULL (not needed).
- *   g_bstride: batch stride of grad_out/out_act in elements, 0 = dense. */
+ *   forward output).  df1 or df2 may be NULL (not needed).
+ *   g_bstride / act_bstride: batch strides of grad_out / out_act in elements, 0 = dense.  The gradient of a
+ *   cost volume that was concatenated into a wider tensor (cost_volume_flow_net.py:176-180) arrives as a channel
+ *   slice of the concat gradient: dense per batch item, wider batch stride -- it is consumed in place. */
 int ocf_corr_bwd(const float* grad_out, const float* out_act, const float* f1, const float* f2,
                  float* df1, float* df2, int B, int C, int H, int W, int d, long long g_bstride,
-                 float leaky_slope, ocf_stream_t stream);
+                 long long act_bstride, float leaky_slope, ocf_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Feature normalisation.  Replaces normalize_features(feature_list, normalize, center,

@@ -19,7 +19,7 @@ c_s = ctypes.c_void_p  # cudaStream_t
 # (tests/test_abi.py cross-checks this table against the header).
 SIGNATURES = {
     "ocf_corr_fwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_ll, c_fl, c_f, c_s],
-    "ocf_corr_bwd": [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_ll, c_fl, c_s],
+    "ocf_corr_bwd": [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_ll, c_ll, c_fl, c_s],
     "ocf_normalize_fwd": [c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_s],
     "ocf_normalize_bwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_s],
     "ocf_warp_fwd": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_s],

@@ -55,12 +55,14 @@ __device__ __forceinline__ unsigned long long ocf_now() {
   return t;
 }
 #define OCF_TL(slot) do { if (threadIdx.x == 0 && blockIdx.x < 1024) ocf_tl[blockIdx.x * 16 + (slot)] = ocf_now(); } while (0)
+#define OCF_TLX(cond, slot) do { if ((cond) && blockIdx.x < 1024) ocf_tl[blockIdx.x * 16 + (slot)] = ocf_now(); } while (0)
 #define OCF_TL_SM() do { if (threadIdx.x == 0 && blockIdx.x < 1024) { unsigned sm; asm("mov.u32 %0, %smid;" : "=r"(sm)); ocf_tl[blockIdx.x * 16 + 15] = sm; } } while (0)
 extern "C" int ocf_debug_timeline(unsigned long long* host, int n) {
   return (int)cudaMemcpyFromSymbol(host, ocf_tl, sizeof(unsigned long long) * n);
 }
 #else
 #define OCF_TL(slot) do { } while (0)
+#define OCF_TLX(cond, slot) do { } while (0)
 #define OCF_TL_SM() do { } while (0)
 #endif
 
@@ -623,34 +625,29 @@ corr_fwd_generic(const float* __restrict__ f1, const float* __restrict__ f2, flo
 // ---- backward -----------------------------------------------------------------------------------
 // mode 0: dout = d f1, fo = f2 ; mode 1: dout = d f2, fo = f1.
 // blockIdx.z = (b * nmodes + slot) * ksplit + channel slice.
-//
-// Per thread: part[p] = sum_dx G[dx][p] * w[p + dx] for its PX pixels and its dy.  Issued as packed FFMA2 with two
-// accumulator sets: even dx pairs the pixels (0,1)(2,3).. with the window pairs (p+dx, p+dx+1), odd dx pairs (1,2)(3,4)..
-// (again p + dx even, i.e. an aligned register pair of the window) and keeps pixels 0 and PX-1 in scalar FFMAs.  The 81
-// coefficients live in registers for the whole kernel, already laid out as those pairs; they are fetched with 128-bit
-// global loads straight into registers WHILE the first feature chunks are in flight (no staging pass, no extra shared memory).
 template <class T, int CR, int STG>
-__global__ void __maxnreg__(96)
-corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2, const float* __restrict__ g,
+__global__ void __launch_bounds__(Threads<T, STG>::value, 2)
+corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
+               const __grid_constant__ CUtensorMap mapg, const __grid_constant__ CUtensorMap mapa, const float* __restrict__ g,
                const float* __restrict__ oact, const float* __restrict__ f1, const float* __restrict__ f2, float* __restrict__ df1,
-               float* __restrict__ df2, int C, int H, int W, long long g_bstride, float inv_c, float slope, int nmodes,
-               int first_mode, int ksplit) {
+               float* __restrict__ df2, int C, int H, int W, long long g_bstride, long long a_bstride, float inv_c, float slope,
+               int nmodes, int first_mode, int ksplit) {
   constexpr int D = T::D, PX = T::PX, ND = T::ND, TH = T::TH, TW = T::TW, CC = T::CC, STAGES = T::STAGES;
   constexpr int S1 = T::S1, S2 = T::S2, F2H = T::F2H, F2W = T::F2W, WIN = T::WIN;
   constexpr bool TMA = STG == STG_TMA;
   constexpr bool VEC = STG != STG_ASYNC4;
-  constexpr int NE = D + 1, NO = D;        // number of even / odd horizontal displacements
-  constexpr int PE = PX / 2, PO = PX / 2 - 1;  // pixel pairs per even / odd displacement
   static_assert(CC % CR == 0, "CC must be a multiple of CR");
-  static_assert(PX == 8 && D % 2 == 0, "pair layout below assumes 8 pixels per thread and an even displacement radius");
   extern __shared__ __align__(128) float smem[];
-  __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES];
+  __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES], g_bar, gdone_bar;
   float* red = smem + STAGES * T::F2_STAGE;  // [ND][CR][TH][S1]
+  // TMA variant: the 81 coefficient planes of the tile are staged through shared memory first (one {GW, TH, ND} box per
+  // dy-warp, GW == 12 mod 32 floats so the 128-bit reads are conflict-free); the area is then reused by the ring + red.
+  constexpr int GW = T::S2, BOXG = ND * TH * GW;
 
   const int tid = threadIdx.x;
   const int lane = tid % T::LANES;
   const int tx = lane % T::TXT, ty = lane / T::TXT;
-  const int dyi = tid / T::LANES;
+  const int dyi = tid / T::LANES;  // == ND for the TMA producer warp
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
   const int zz = blockIdx.z / ksplit, ks = blockIdx.z - zz * ksplit;
   const int b = zz / nmodes;
@@ -659,115 +656,117 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
   const int nchunks = cr.count;
   float* dout = (mode == 0 ? df1 : df2) + (size_t)b * C * H * W;
   const size_t gb = (g_bstride ? (size_t)g_bstride : (size_t)ND * ND * H * W) * b;
-  const float* fo = (mode == 0 ? f2 : f1) + (size_t)b * C * H * W;
+  const size_t ab = (a_bstride ? (size_t)a_bstride : (size_t)ND * ND * H * W) * b;
 
-  // ---- start the feature ring first: its latency overlaps the coefficient loads below ----
-  constexpr unsigned BYTES = sizeof(float) * T::F2_STAGE;
-  auto issue_tma = [&](int i) {
-    const int s = i % STAGES;
-    const CUtensorMap* map = mode == 0 ? &map2 : &map1;  // the OTHER feature
-    mbar_expect_tx(&full_bar[s], BYTES);
-    tma_load_4d(smem + s * T::F2_STAGE, map, &full_bar[s], x0 - D, y0 - D, (cr.begin + i) * CC, b);
-  };
-  auto issue = [&](int i) {
-    stage_box_async<CC, F2H, F2W, S2, T::THREADS, STG == STG_ASYNC16>(smem + (i % STAGES) * T::F2_STAGE, fo, (cr.begin + i) * CC, C, H, W,
-                                                                      y0 - D, x0 - D);
-  };
+  float G[ND][PX];  // 81 per-pixel coefficients of this thread's dy row, kept in registers for the whole kernel
   if constexpr (TMA) {
     if (tid == 0) {
 #pragma unroll
       for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ND); }
+      mbar_init(&g_bar, 1);
+      mbar_init(&gdone_bar, ND);
       mbar_fence_init();
-#pragma unroll
-      for (int s = 0; s < STAGES; ++s)
-        if (s < nchunks) issue_tma(s);
     }
-  } else {
+    __syncthreads();
+    const bool has_act = oact != nullptr;
+    if (dyi == ND) {
+      if (lane == 0) {
+        // coefficient boxes: mode 0 -> planes dy*ND.. at (y0, x0) ; mode 1 -> planes (2D-dy)*ND.. at (y0+dy-D, x0-D)
+        constexpr unsigned GBYTES = sizeof(float) * ND * BOXG;
+        for (int pass = 0; pass < (has_act ? 2 : 1); ++pass) {
+          if (pass == 1) mbar_wait(&gdone_bar, 0);  // every warp has lifted its coefficients out of the staging area
+          mbar_expect_tx(&g_bar, GBYTES);
+          for (int w = 0; w < ND; ++w) {
+            const int plane0 = mode == 0 ? w * ND : (2 * D - w) * ND;
+            tma_load_4d(smem + w * BOXG, pass == 0 ? &mapg : &mapa, &g_bar, mode == 0 ? x0 : x0 - D, mode == 0 ? y0 : y0 + w - D, plane0, b);
+          }
+        }
+        mbar_wait(&gdone_bar, has_act ? 1 : 0);  // staging area is free: start feeding the feature ring
+        constexpr unsigned BYTES = sizeof(float) * T::F2_STAGE;
+        const CUtensorMap* map = mode == 0 ? &map2 : &map1;  // the OTHER feature
+        for (int i = 0; i < nchunks; ++i) {
+          const int s = i % STAGES;
+          if (i >= STAGES) mbar_wait(&empty_bar[s], ((i / STAGES) - 1) & 1);
+          mbar_expect_tx(&full_bar[s], BYTES);
+          tma_load_4d(smem + s * T::F2_STAGE, map, &full_bar[s], x0 - D, y0 - D, (cr.begin + i) * CC, b);
+        }
+      }
+      return;  // the producer warp takes no part in the compute-warp barriers below
+    }
+    const float* gw = smem + dyi * BOXG + ty * GW + tx * PX;
+    for (int pass = 0; pass < (has_act ? 2 : 1); ++pass) {
+      mbar_wait(&g_bar, pass);
+      if (mode == 0) {
+#pragma unroll
+        for (int dx = 0; dx < ND; ++dx) {
+          float t[PX];
+#pragma unroll
+          for (int q = 0; q < PX / 4; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(gw + dx * TH * GW + 4 * q);
+            t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
+          }
+#pragma unroll
+          for (int p = 0; p < PX; ++p) {
+            if (pass == 0) G[dx][p] = t[p];
+            else if (!(t[p] > 0.f)) G[dx][p] *= slope;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int dx = 0; dx < ND; ++dx) {
+          float t[PX + 4];
+#pragma unroll
+          for (int q = 0; q < PX / 4 + 1; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(gw + (2 * D - dx) * TH * GW + (dx & ~3) + 4 * q);
+            t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
+          }
+#pragma unroll
+          for (int p = 0; p < PX; ++p) {
+            const float v = t[p + (dx & 3)];
+            if (pass == 0) G[dx][p] = v;
+            else if (!(v > 0.f)) G[dx][p] *= slope;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&gdone_bar);
+    }
+  }
+  const float* fo = (mode == 0 ? f2 : f1) + (size_t)b * C * H * W;
+  auto issue = [&](int i) {
+    stage_box_async<CC, F2H, F2W, S2, T::THREADS, STG == STG_ASYNC16>(smem + (i % STAGES) * T::F2_STAGE, fo, (cr.begin + i) * CC, C, H, W,
+                                                                      y0 - D, x0 - D);
+  };
+  if constexpr (!TMA) {
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
       if (s < nchunks) issue(s);
       cp_async_commit();
     }
-  }
-
-  // ---- the 81 coefficients of this thread's dy row (LeakyReLU mask of the forward folded in) ----
-  // mode 0: G[dx][p] = g[k(dy,dx)][y][xs+p] ; mode 1: G[dx][p] = g[k(-dy,-dx)][y+dy][xs+p+dx]
-  float G[ND][PX];
-  auto load_coefficients = [&](auto mode_c) {
-    constexpr int mode = decltype(mode_c)::value;
     const int y = y0 + ty, xs = x0 + tx * PX;
 #pragma unroll
     for (int dx = 0; dx < ND; ++dx) {
+      // mode 0: plane k(dy,dx) at (y, x) ; mode 1: plane k(-dy,-dx) at (y+dy, x+dx)
       const int k = mode == 0 ? dyi * ND + dx : (2 * D - dyi) * ND + (2 * D - dx);
       const int sy = mode == 0 ? y : y + dyi - D;
+      const int sx0 = mode == 0 ? xs : xs + dx - D;
       const size_t off = gb + ((size_t)k * H + sy) * W;
-      const bool rowok = sy >= 0 && sy < H;
-      if (VEC) {
-        // aligned 128-bit loads; W % 4 == 0 so every float4 is entirely inside or outside the row
-        constexpr int NV = PX / 4 + 1;
-        const int sh = mode == 0 ? 0 : dx - D;        // horizontal shift of the coefficient row
-        const int base = xs + (sh & ~3);                  // floor to a multiple of 4 (two's complement: also for negatives)
-        const int o = sh & 3;
-        float t[4 * NV];
 #pragma unroll
-        for (int q = 0; q < NV; ++q) {
-          const int gx = base + 4 * q;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rowok && gx >= 0 && gx < W && (q < NV - 1 || o != 0)) {
-            v = __ldg(reinterpret_cast<const float4*>(g + off + gx));
-            if (oact != nullptr) {
-              const float4 a = __ldg(reinterpret_cast<const float4*>(oact + off + gx));
-              if (!(a.x > 0.f)) v.x *= slope;
-              if (!(a.y > 0.f)) v.y *= slope;
-              if (!(a.z > 0.f)) v.z *= slope;
-              if (!(a.w > 0.f)) v.w *= slope;
-            }
-          }
-          t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
+      for (int p = 0; p < PX; ++p) {
+        const int sx = sx0 + p;
+        float v = 0.f;
+        if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+          v = __ldg(g + off + sx);
+          if (oact != nullptr && !(__ldg(oact + (off - gb + ab) + sx) > 0.f)) v *= slope;
         }
-#pragma unroll
-        for (int p = 0; p < PX; ++p) {
-          G[dx][p] = t[p + o];
-        }
-      } else {
-        const int sx0 = mode == 0 ? xs : xs + dx - D;
-#pragma unroll
-        for (int p = 0; p < PX; ++p) {
-          const int sx = sx0 + p;
-          float v = 0.f;
-          if (rowok && sx >= 0 && sx < W) {
-            v = __ldg(g + off + sx);
-            if (oact != nullptr && !(__ldg(oact + off + sx) > 0.f)) v *= slope;
-          }
-          G[dx][p] = v;
-        }
+        G[dx][p] = v;
       }
     }
-  };
-  if (mode == 0) load_coefficients(IntC<0>{}); else load_coefficients(IntC<1>{});
-  // pair layout for FFMA2
-  u64 GE[NE][PE], GO[NO][PO];
-  float G0[NO], G7[NO];
-#pragma unroll
-  for (int e = 0; e < NE; ++e)
-#pragma unroll
-    for (int j = 0; j < PE; ++j) GE[e][j] = pack2(G[2 * e][2 * j], G[2 * e][2 * j + 1]);
-#pragma unroll
-  for (int o = 0; o < NO; ++o) {
-#pragma unroll
-    for (int j = 0; j < PO; ++j) GO[o][j] = pack2(G[2 * o + 1][2 * j + 1], G[2 * o + 1][2 * j + 2]);
-    G0[o] = G[2 * o + 1][0];
-    G7[o] = G[2 * o + 1][PX - 1];
   }
-  if constexpr (TMA) __syncthreads();  // barrier initialisation visible to every thread before the first wait
 
   for (int i = 0; i < nchunks; ++i) {
     const int s = i % STAGES;
     if constexpr (TMA) {
-      if (tid == 0 && i >= 1 && i - 1 + STAGES < nchunks) {  // deferred refill of the stage released one iteration ago
-        mbar_wait(&empty_bar[(i - 1) % STAGES], ((i - 1) / STAGES) & 1);
-        issue_tma(i - 1 + STAGES);
-      }
       mbar_wait(&full_bar[s], (i / STAGES) & 1);
     } else {
       cp_async_wait<STAGES - 2>();
@@ -782,53 +781,24 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
       if (c0 + r0 >= C) break;  // uniform across the block
 #pragma unroll
       for (int c = 0; c < CR; ++c) {
-        u64 w2[WIN / 2];
+        float w[WIN], part[PX];
 #pragma unroll
         for (int q = 0; q < WIN / 4; ++q) {
-          const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(pw + (r0 + c) * F2H * S2 + 4 * q);
-          w2[2 * q] = v.x; w2[2 * q + 1] = v.y;
+          const float4 v = *reinterpret_cast<const float4*>(pw + (r0 + c) * F2H * S2 + 4 * q);
+          w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
         }
-        u64 pe[PE], po[PO];
-        float s0 = 0.f, s7 = 0.f;
 #pragma unroll
-        for (int j = 0; j < PE; ++j) pe[j] = 0ull;
+        for (int p = 0; p < PX; ++p) part[p] = 0.f;
 #pragma unroll
-        for (int j = 0; j < PO; ++j) po[j] = 0ull;
+        for (int dx = 0; dx < ND; ++dx)
 #pragma unroll
-        for (int e = 0; e < NE; ++e)  // dx = 2e: pixels (2j, 2j+1) x window (2j+2e, 2j+2e+1)
-#pragma unroll
-          for (int j = 0; j < PE; ++j) ffma2(pe[j], GE[e][j], w2[j + e]);
-#pragma unroll
-        for (int o = 0; o < NO; ++o) {  // dx = 2o+1: pixels (2j+1, 2j+2) x window (2j+2o+2, 2j+2o+3)
-#pragma unroll
-          for (int j = 0; j < PO; ++j) ffma2(po[j], GO[o][j], w2[j + o + 1]);
-          float lo, hi;
-          unpack2(w2[o], lo, hi);                 // pixel 0: window element 2o+1
-          s0 = fmaf(G0[o], hi, s0);
-          unpack2(w2[(PX + 2 * o) / 2], lo, hi);  // pixel PX-1: window element PX-1 + 2o+1 = PX + 2o
-          s7 = fmaf(G7[o], lo, s7);
-        }
-        float part[PX];
-        {
-          float elo[PE], ehi[PE], olo[PO], ohi[PO];
-#pragma unroll
-          for (int j = 0; j < PE; ++j) unpack2(pe[j], elo[j], ehi[j]);
-#pragma unroll
-          for (int j = 0; j < PO; ++j) unpack2(po[j], olo[j], ohi[j]);
-          part[0] = elo[0] + s0;
-          part[PX - 1] = ehi[PE - 1] + s7;
-#pragma unroll
-          for (int j = 0; j < PO; ++j) {
-            part[2 * j + 1] = ehi[j] + olo[j];
-            part[2 * j + 2] = elo[j + 1] + ohi[j];
-          }
-        }
+          for (int p = 0; p < PX; ++p) part[p] = fmaf(G[dx][p], w[p + dx], part[p]);
         float* rp = red + ((dyi * CR + c) * TH + ty) * S1 + tx * PX;
 #pragma unroll
         for (int q = 0; q < PX / 4; ++q)
           *reinterpret_cast<float4*>(rp + 4 * q) = make_float4(part[4 * q], part[4 * q + 1], part[4 * q + 2], part[4 * q + 3]);
       }
-      __syncthreads();
+      if constexpr (TMA) consumer_bar_sync<T::THREADS>(); else __syncthreads();
       // cross-dy reduction: CR*TH*TW/4 float4 outputs
       constexpr int OUT4 = CR * TH * TW / 4;
       for (int j = tid; j < OUT4; j += T::THREADS) {
@@ -853,10 +823,10 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
           }
         }
       }
-      __syncthreads();
+      if constexpr (TMA) consumer_bar_sync<T::THREADS>(); else __syncthreads();
     }
     if constexpr (TMA) {
-      // the last barrier above ordered every warp's reads of this stage: one arrival per warp frees it
+      // the last consumer barrier above ordered every warp's reads of this stage: one arrival per warp frees it
       if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
   }
@@ -867,13 +837,14 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
 __global__ void __launch_bounds__(128)
 corr_bwd_generic(const float* __restrict__ g, const float* __restrict__ oact, const float* __restrict__ f1,
                  const float* __restrict__ f2, float* __restrict__ df1, float* __restrict__ df2, int C, int H, int W, int d,
-                 long long g_bstride, float inv_c, float slope) {
+                 long long g_bstride, long long a_bstride, float inv_c, float slope) {
   const int nd = 2 * d + 1;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= H * W) return;
   const int y = pix / W, x = pix - y * W;
   const int c = blockIdx.y, b = blockIdx.z;
   const size_t gb = (g_bstride ? (size_t)g_bstride : (size_t)nd * nd * H * W) * b;
+  const size_t ab = (a_bstride ? (size_t)a_bstride : (size_t)nd * nd * H * W) * b;
   const size_t fb = ((size_t)b * C + c) * H * W;
   float a1 = 0.f, a2 = 0.f;
   for (int dyi = 0; dyi < nd; ++dyi) {
@@ -886,7 +857,7 @@ corr_bwd_generic(const float* __restrict__ g, const float* __restrict__ oact, co
       if (df1 != nullptr && yy >= 0 && yy < H && xx >= 0 && xx < W) {
         const size_t go = gb + ((size_t)k * H + y) * W + x;
         float gv = __ldg(g + go);
-        if (oact != nullptr && !(__ldg(oact + go) > 0.f)) gv *= slope;
+        if (oact != nullptr && !(__ldg(oact + (go - gb + ab)) > 0.f)) gv *= slope;
         a1 = fmaf(gv, __ldg(f2 + fb + (size_t)yy * W + xx), a1);
       }
       // d f2: g[k, y-dy, x-dx] * f1[y-dy, x-dx]
@@ -894,7 +865,7 @@ corr_bwd_generic(const float* __restrict__ g, const float* __restrict__ oact, co
       if (df2 != nullptr && ys >= 0 && ys < H && xs >= 0 && xs < W) {
         const size_t go = gb + ((size_t)k * H + ys) * W + xs;
         float gv = __ldg(g + go);
-        if (oact != nullptr && !(__ldg(oact + go) > 0.f)) gv *= slope;
+        if (oact != nullptr && !(__ldg(oact + (go - gb + ab)) > 0.f)) gv *= slope;
         a2 = fmaf(gv, __ldg(f1 + fb + (size_t)ys * W + xs), a2);
       }
     }
@@ -1035,20 +1006,21 @@ extern "C" int ocf_corr_fwd(const float* f1, const float* f2, float* out, int B,
 }
 
 extern "C" int ocf_corr_bwd(const float* grad_out, const float* out_act, const float* f1, const float* f2, float* df1,
-                            float* df2, int B, int C, int H, int W, int d, long long g_bstride, float leaky_slope,
-                            ocf_stream_t stream) {
+                            float* df2, int B, int C, int H, int W, int d, long long g_bstride, long long act_bstride,
+                            float leaky_slope, ocf_stream_t stream) {
   OCF_REQUIRE_PTR(grad_out); OCF_REQUIRE_PTR(f1); OCF_REQUIRE_PTR(f2);
   OCF_REQUIRE(df1 != nullptr || df2 != nullptr, OCF_ENULL);
   OCF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, OCF_ESHAPE);
   OCF_REQUIRE(d >= 0 && d <= OCF_MAX_DISPLACEMENT, OCF_EUNSUPPORTED);
   const long long nd = 2 * d + 1;
   OCF_REQUIRE(g_bstride == 0 || g_bstride >= nd * nd * H * W, OCF_ESHAPE);
+  OCF_REQUIRE(act_bstride == 0 || act_bstride >= nd * nd * H * W, OCF_ESHAPE);
   OCF_REQUIRE(B <= 4095 && C <= 65535, OCF_EUNSUPPORTED);
   cudaStream_t s = ocf_cast_stream(stream);
   const float inv_c = 1.0f / (float)C;
   if (d == 4) {
     using T = Tile4;
-    const size_t smem = sizeof(float) * (T::STAGES * T::F2_STAGE + T::ND * BWD_CR * T::TH * T::S1);
+    size_t smem = sizeof(float) * (T::STAGES * T::F2_STAGE + T::ND * BWD_CR * T::TH * T::S1);
     const int nmodes = (df1 != nullptr && df2 != nullptr) ? 2 : 1;
     const int first = df1 != nullptr ? 0 : 1;
     const int gx = (W + T::TW - 1) / T::TW, gy = (H + T::TH - 1) / T::TH;
@@ -1056,26 +1028,33 @@ extern "C" int ocf_corr_bwd(const float* grad_out, const float* out_act, const f
     dim3 grid(gx, gy, B * nmodes * ks);
     const bool vec = (W % 4 == 0) && ocf_aligned16(f1) && ocf_aligned16(f2) && (df1 == nullptr || ocf_aligned16(df1)) &&
                      (df2 == nullptr || ocf_aligned16(df2));
-    CUtensorMap m1, m2;
+    CUtensorMap m1, m2, mg, ma;
     memset(&m1, 0, sizeof(m1));
     memset(&m2, 0, sizeof(m2));
+    memset(&mg, 0, sizeof(mg));
+    memset(&ma, 0, sizeof(ma));
     const long long gbs = g_bstride ? g_bstride : nd * nd * H * W;
-    const bool gvec = ocf_aligned16(grad_out) && (out_act == nullptr || ocf_aligned16(out_act)) && (gbs % 4 == 0);
-    const bool tma = vec && gvec && make_map(&m1, f1, B, C, H, W, T::S2, T::F2H, T::CC) && make_map(&m2, f2, B, C, H, W, T::S2, T::F2H, T::CC);
+    const long long abs_ = act_bstride ? act_bstride : nd * nd * H * W;
+    bool tma = vec && ocf_aligned16(grad_out) && (out_act == nullptr || ocf_aligned16(out_act)) && (gbs % 4 == 0) && (abs_ % 4 == 0);
+    tma = tma && make_map(&m1, f1, B, C, H, W, T::S2, T::F2H, T::CC) && make_map(&m2, f2, B, C, H, W, T::S2, T::F2H, T::CC) &&
+          make_map(&mg, grad_out, B, (int)(nd * nd), H, W, T::S2, T::TH, T::ND, gbs) &&
+          (out_act == nullptr || make_map(&ma, out_act, B, (int)(nd * nd), H, W, T::S2, T::TH, T::ND, abs_));
     if (tma) {
+      const size_t gstage = sizeof(float) * T::ND * T::ND * T::TH * T::S2;  // coefficient staging, reused by ring + red
+      if (gstage > smem) smem = gstage;
       auto kernel = corr_bwd_tiled<T, BWD_CR, STG_TMA>;
       if (int e = set_smem(kernel, smem)) return e;
-      if (int e = launch_kernel(kernel, grid, T::THREADS, smem, s, 1, m1, m2, grad_out, out_act, f1, f2, df1, df2, C, H, W, g_bstride,
-                                inv_c, leaky_slope, nmodes, first, ks)) return e;
+      if (int e = launch_kernel(kernel, grid, T::THREADS + 32, smem, s, 1, m1, m2, mg, ma, grad_out, out_act, f1, f2, df1, df2, C, H, W, g_bstride,
+                                act_bstride, inv_c, leaky_slope, nmodes, first, ks)) return e;
     } else {
-      auto kernel = (vec && gvec) ? corr_bwd_tiled<T, BWD_CR, STG_ASYNC16> : corr_bwd_tiled<T, BWD_CR, STG_ASYNC4>;
+      auto kernel = vec ? corr_bwd_tiled<T, BWD_CR, STG_ASYNC16> : corr_bwd_tiled<T, BWD_CR, STG_ASYNC4>;
       if (int e = set_smem(kernel, smem)) return e;
-      if (int e = launch_kernel(kernel, grid, T::THREADS, smem, s, 1, m1, m2, grad_out, out_act, f1, f2, df1, df2, C, H, W, g_bstride,
-                                inv_c, leaky_slope, nmodes, first, ks)) return e;
+      if (int e = launch_kernel(kernel, grid, T::THREADS, smem, s, 1, m1, m2, mg, ma, grad_out, out_act, f1, f2, df1, df2, C, H, W, g_bstride,
+                                act_bstride, inv_c, leaky_slope, nmodes, first, ks)) return e;
     }
   } else {
     dim3 grid((H * W + 127) / 128, C, B);
-    corr_bwd_generic<<<grid, 128, 0, s>>>(grad_out, out_act, f1, f2, df1, df2, C, H, W, d, g_bstride, inv_c, leaky_slope);
+    corr_bwd_generic<<<grid, 128, 0, s>>>(grad_out, out_act, f1, f2, df1, df2, C, H, W, d, g_bstride, act_bstride, inv_c, leaky_slope);
   }
   return ocf_launch_status();
 }

@@ -58,13 +58,24 @@ class _CostVolume(torch.autograd.Function):
         f1, f2 = saved[0], saved[1]
         act = saved[2] if len(saved) == 3 else None
         B, C, H, W = f1.shape
-        g = g.contiguous()
+        # The incoming gradient is usually a channel slice of the decoder's concat gradient (CatBackward hands out
+        # `narrow` views): dense per batch item, only the batch stride differs.  The C ABI takes that stride, so the
+        # slice is consumed in place instead of being re-packed by a 2 x 81 x H x W copy per level.
+        K = g.shape[1]
+        g_bstride = 0
+        if not g.is_contiguous():
+            st = g.stride()
+            if (st[3] == 1 and st[2] == W and st[1] == H * W and st[0] >= K * H * W and st[0] % 4 == 0
+                    and g.data_ptr() % 16 == 0 and g.dtype == torch.float32):
+                g_bstride = st[0]
+            else:
+                g = g.contiguous()
         need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         df1 = torch.empty_like(f1) if need1 else None
         df2 = torch.empty_like(f2) if need2 else None
         if need1 or need2:
             with torch.cuda.device_of(f1):
-                _lib.call("ocf_corr_bwd", _p(g), _p(act), _p(f1), _p(f2), _p(df1), _p(df2), B, C, H, W, ctx.d, 0, ctx.slope, _stream())
+                _lib.call("ocf_corr_bwd", _p(g), _p(act), _p(f1), _p(f2), _p(df1), _p(df2), B, C, H, W, ctx.d, g_bstride, 0, ctx.slope, _stream())
         return df1, df2, None, None
 
 

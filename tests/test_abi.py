@@ -51,7 +51,7 @@ def test_argument_validation_happens_before_any_launch():
     assert lib.ocf_corr_fwd(one, one, one, 0, 1, 1, 1, 4, 0, 1.0, None, None) == -2
     assert lib.ocf_corr_fwd(one, one, one, 1, 1, 1, 1, 17, 0, 1.0, None, None) == -3
     assert lib.ocf_corr_fwd(one, one, one, 1, 1, 2, 2, 4, 5, 1.0, None, None) == -2  # out_bstride too small
-    assert lib.ocf_corr_bwd(one, None, one, one, None, None, 1, 1, 1, 1, 4, 0, 1.0, None) == -1
+    assert lib.ocf_corr_bwd(one, None, one, one, None, None, 1, 1, 1, 1, 4, 0, 0, 1.0, None) == -1
     assert lib.ocf_warp_fwd(one, one, None, one, 1, 1, 1, 1, 8, 1.0, None) == -3
     assert lib.ocf_warp_bwd(one, one, one, None, None, None, None, 1, 1, 1, 1, 0, 1.0, None) == -1
     assert lib.ocf_range_map(one, None, None, 1, 1, 1, None) == -1

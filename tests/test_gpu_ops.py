@@ -217,3 +217,27 @@ def test_cuda_rejects_cpu_and_bad_args():
     with pytest.raises(RuntimeError):
         ocf.compute_cost_volume(torch.zeros(1, 2, 3, 3, device="cuda"), torch.zeros(1, 2, 3, 3, device="cuda"), 17)
     assert _lib.load().ocf_corr_fwd(None, None, None, 1, 1, 1, 1, 4, 0, 1.0, None, None) == -1
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 24, 32), (1, 16, 9, 13)])
+def test_corr_backward_consumes_concat_gradient_slice_in_place(shape):
+    """cost_volume_flow_net.py:173-180: LeakyReLU(corr) is concatenated with other maps, so its gradient arrives as a
+    channel slice (dense per item, wider batch stride).  ocf_corr_bwd takes that stride; results must equal the oracle."""
+    from ocflow_b200 import ops
+
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(77)
+    f1, f2 = torch.randn(B, C, H, W, generator=g), torch.randn(B, C, H, W, generator=g)
+    other = torch.randn(B, 7, H, W, generator=g)
+    cot = torch.randn(B, 7 + 81 + 7, H, W, generator=g)
+
+    def run(corr, dev):
+        a, b, o = (t.clone().to(dev).requires_grad_(True) for t in (f1, f2, other))
+        cat = torch.cat((o, corr(a, b), o * 2), 1)
+        (cat * cot.to(dev)).sum().backward()
+        return a.grad, b.grad
+
+    mine = run(lambda a, b: ops.cost_volume(a, b, 4, 0.1), "cuda")
+    want = run(lambda a, b: torch.nn.functional.leaky_relu(O.cost_volume(a, b, 4), 0.1), "cpu")
+    for m, w in zip(mine, want):
+        assert_close(m, w, TOL, "corr grad through a concat slice")

@@ -35,11 +35,11 @@ rows = [r for r in rows if r[0]]
 t0 = min(r[0] for r in rows)
 print("ctas", len(rows), "span_us %.2f" % ((max(r[14] for r in rows) - t0) / 1e3))
 def rel(v): return "%7.2f" % ((v - t0) / 1e3) if v else "      -"
-print("cta sm  start first_data t0_done t0_stored t1_done t1_stored t2_done t2_stored end")
+print("cta sm  slots 0..9, 14")
 for i, r in enumerate(rows):
     if i < 12 or i % 37 == 0 or i >= len(rows) - 4:
-        print("%4d %3d" % (i, r[15]), rel(r[0]), rel(r[1]), rel(r[2]), rel(r[3]), rel(r[4]), rel(r[5]), rel(r[6]), rel(r[7]), rel(r[14]))
+        print("%4d %3d" % (i, r[15]), *[rel(r[q]) for q in range(10)], rel(r[14]))
 import statistics
-for k, nm in ((0, "start"), (1, "first_data"), (2, "t0_done"), (3, "t0_stored"), (14, "end")):
-    v = [(r[k] - t0) / 1e3 for r in rows if r[k]]
+for k, nm in [(q, "slot%d" % q) for q in range(10)] + [(14, "end")]:
+    v = [(r[k] - t0) / 1e3 for r in rows if r[k]] or [0]
     print("%-10s min %.2f median %.2f max %.2f" % (nm, min(v), statistics.median(v), max(v)))
