@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--kernels-only", action="store_true", help="only time the hot-path kernels alone (developer aid)")
     ap.add_argument("--cuda-profiler-range", action="store_true",
                     help="bracket the timed region with cudaProfilerStart/Stop (use with ncu --profile-from-start off)")
+    ap.add_argument("--only", default="", help="kernels-only: time only the kernels whose name contains this substring")
     ap.add_argument("--levels", default="", help="kernels-only: comma list of C:h:w overriding the pyramid levels (e.g. 16:188:621)")
     return ap.parse_args()
 
@@ -245,6 +246,9 @@ def kernel_table(args, torch):
 
 def time_kernels(args, torch, with_copy_ref=False):
     table = kernel_table(args, torch)
+    only = getattr(args, "only", "")
+    if only:
+        table = {k: v for k, v in table.items() if any(o in k for o in only.split(","))}
     flush = torch.empty(1024 * 1024 * 1024 // 4, device="cuda")  # 1 GiB >> 126 MB L2; its memset also keeps the GPU busy while the timed launch is enqueued
     if with_copy_ref:
         # the practical streaming ceiling AT THIS SIZE: a plain device copy moving the same number of bytes, same harness
@@ -376,12 +380,21 @@ def main():
     dte = float(dte)
 
     def finish():
-        # every rank leaves together: a rank that tears its communicator down (or exits) while rank 0 is still measuring
-        # the roofline leg leaves rank 0's own teardown waiting on a peer that is gone
+        # Every rank leaves together and WITHOUT tearing the NCCL communicator down: the step's CUDA graph holds the
+        # captured all-reduce, and destroy_process_group() under that graph does not return (observed on B200 x2).
+        # Ranks > 0 wait (file flag, no collective) until rank 0 has printed its line, then all exit hard with status 0.
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.barrier()
+            flag = "/tmp/ocflow_b200_bench_done_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getppid())
+            if rank == 0:
+                open(flag, "w").close()
+            else:
+                t_end = time.time() + 600
+                while not os.path.exists(flag) and time.time() < t_end:
+                    time.sleep(0.05)
             torch.cuda.synchronize()
-            dist.destroy_process_group()
+            os._exit(0)
 
     if rank != 0:
         finish()

@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libocflow_b200.so")
+# OCFLOW_B200_LIB: developer override used by the tuning scripts in tools/ to load an alternative build of the SAME library
+LIB_PATH = os.environ.get("OCFLOW_B200_LIB") or os.path.join(_PKG, "libocflow_b200.so")
 
 c_f = ctypes.c_void_p  # device (or host) float* / double* passed as raw addresses
 c_i = ctypes.c_int

@@ -10,6 +10,13 @@
 namespace {
 
 constexpr int LT = 256;
+// fused loss tuning knobs: pixels per thread (vector path) and grid cap in CTAs per SM
+#ifndef OCF_OPF_VPX
+#define OCF_OPF_VPX 4
+#endif
+#ifndef OCF_OPF_CAP
+#define OCF_OPF_CAP 4
+#endif
 
 __device__ __forceinline__ float rho(float x, float a2) { return sqrtf(fmaf(x, x, a2)); }
 
@@ -203,6 +210,9 @@ __device__ __forceinline__ PixVec<VPX> ld_vec(const float* p) {
   if (VPX == 4) {
     const float4 t = *reinterpret_cast<const float4*>(p);
     r.v[0] = t.x; r.v[1 % VPX] = t.y; r.v[2 % VPX] = t.z; r.v[3 % VPX] = t.w;
+  } else if (VPX == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    r.v[0] = t.x; r.v[1 % VPX] = t.y;
   } else {
 #pragma unroll
     for (int i = 0; i < VPX; ++i) r.v[i] = p[i];
@@ -214,6 +224,8 @@ template <int VPX>
 __device__ __forceinline__ void st_vec(float* p, const PixVec<VPX>& r) {
   if (VPX == 4) {
     *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1 % VPX], r.v[2 % VPX], r.v[3 % VPX]);
+  } else if (VPX == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(r.v[0], r.v[1 % VPX]);
   } else {
 #pragma unroll
     for (int i = 0; i < VPX; ++i) p[i] = r.v[i];
@@ -465,16 +477,16 @@ extern "C" int ocf_occ_photo_fused(const float* img1, const float* img2, const f
   const float* opt[5] = {range_map, flow_gt, occ_gt, dflow_unit, warped_out};
   for (const float* p : opt) vec = vec && (p == nullptr || ocf_aligned16(p));
   OCF_REQUIRE((long long)C * H * W < (1LL << 31) && B <= 65535, OCF_EUNSUPPORTED);
-  const int vpx = vec ? 4 : 1;
+  const int vpx = vec ? OCF_OPF_VPX : 1;
   const int gpi = H * W / vpx;
-  // blocks per image: whole grid ~ 2 CTAs x 148 SMs x 2 waves, each thread doing >= 1 group
+  // blocks per image: every thread owns at most a few pixel groups; the grid is capped at OCF_OPF_CAP CTAs per SM
   int bx = (gpi + LT - 1) / LT;
-  const int cap = (4 * OCF_SM_COUNT + B - 1) / B;
+  const int cap = (OCF_OPF_CAP * OCF_SM_COUNT + B - 1) / B;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   dim3 grid(bx, B);
   if (vec)
-    occ_photo_fused_kernel<4><<<grid, LT, 0, s>>>(img1, img2, flow, range_map, flow_gt, occ_gt, sums, dflow_unit, warped_out, C, H, W, alpha * alpha);
+    occ_photo_fused_kernel<OCF_OPF_VPX><<<grid, LT, 0, s>>>(img1, img2, flow, range_map, flow_gt, occ_gt, sums, dflow_unit, warped_out, C, H, W, alpha * alpha);
   else
     occ_photo_fused_kernel<1><<<grid, LT, 0, s>>>(img1, img2, flow, range_map, flow_gt, occ_gt, sums, dflow_unit, warped_out, C, H, W, alpha * alpha);
   return ocf_launch_status();

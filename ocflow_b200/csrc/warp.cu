@@ -59,6 +59,13 @@ __device__ __forceinline__ float cover_of(const Taps& t) {
 __device__ __forceinline__ float mask_of(const Taps& t) { return cover_of(t) < 0.9999f ? 0.f : 1.f; }
 
 constexpr int WARP_THREADS = 256;
+// warp backward tuning knobs: rows per thread and channels whose loads are batched ahead of the atomics
+#ifndef OCF_WB_R
+#define OCF_WB_R 1
+#endif
+#ifndef OCF_WB_CB
+#define OCF_WB_CB 2
+#endif
 
 // grid: (ceil(HW/256), channel slabs, B)
 __global__ void __launch_bounds__(WARP_THREADS)
@@ -179,7 +186,7 @@ warp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ img, c
   const bool need_vals = d_flow != nullptr || d_occ != nullptr;
   // Channels go in batches of CB: all loads of a batch are issued before its first atomic (atomics are ordering points
   // for the compiler, so without the explicit batch every channel would expose a full global-load latency).
-  constexpr int CB = 2;
+  constexpr int CB = OCF_WB_CB;
   for (int c0 = c_begin; c0 < c_end; c0 += CB, ip += (size_t)CB * HW, gp += (size_t)CB * HW) {
     float gv[CB][R], ta[CB][R], tb[CB][R], tc[CB][R], td[CB][R];
 #pragma unroll
@@ -352,7 +359,7 @@ extern "C" int ocf_warp_bwd(const float* grad_out, const float* img, const float
     if (d_flow != nullptr && (e = cudaMemsetAsync(d_flow, 0, sizeof(float) * (size_t)B * 2 * HW, s)) != cudaSuccess) return (int)e;
     if (d_occ != nullptr && (e = cudaMemsetAsync(d_occ, 0, sizeof(float) * (size_t)B * HW, s)) != cudaSuccess) return (int)e;
   }
-  constexpr int R = 2;
+  constexpr int R = OCF_WB_R;
   dim3 grid(((H + R - 1) / R * W + WARP_THREADS - 1) / WARP_THREADS, nslabs, B);
   warp_bwd_kernel<R><<<grid, WARP_THREADS, 0, s>>>(grad_out, img, flow, occ, d_img, d_flow, d_occ, C, H, W, slab, nslabs, flags, scale);
   return ocf_launch_status();
