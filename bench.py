@@ -212,7 +212,7 @@ def kernel_table(args, torch):
             "ocf_corr_bwd", P(gout), P(out), P(f1), P(f2), P(d1), P(d2), B, C, h, w, 4, 0, 0, 0.1, st), 4 * n * (81 + 4 * C), 1)
         # normalisation of the two feature maps of the level (3 kernels fwd, 3 kernels bwd)
         y1, y2 = torch.empty_like(f1), torch.empty_like(f2)
-        stats = torch.empty(8 * 2 * B, device=dev)
+        stats = torch.empty(8 * 2 * B + 8, device=dev)
         red = torch.empty(8 * 2 * B, device=dev)
         xs_arr = (ctypes.c_void_p * 2)(f1.data_ptr(), f2.data_ptr())
         ys_arr = (ctypes.c_void_p * 2)(y1.data_ptr(), y2.data_ptr())

@@ -75,7 +75,7 @@ int ocf_corr_bwd(const float* grad_out, const float* out_act, const float* f1, c
  *   moments_across_channels, moments_across_images)  models/networks/correlation_layer.py:42-82.
  *   All T tensors of the list must share one shape [B,C,H,W] (they do at every call site).
  *   flags: bit0 normalize, bit1 center, bit2 moments_across_channels, bit3 moments_across_images.
- *   stats workspace (device, caller-owned, 8-byte aligned): 8*T*B*G floats, G = 1 (across channels) or C
+ *   stats workspace (device, caller-owned, 8-byte aligned): 8*T*B*G + 8 floats, G = 1 (across channels) or C
  *   -- fp64 partial sums, then per-group {mean, var}, then the {mean, inv_std} actually applied.
  * ------------------------------------------------------------------------------------------- */
 #define OCF_NORM_NORMALIZE 1

@@ -5,17 +5,20 @@
 // averages the per-group means and variances of ALL tensors to a single scalar pair (:66-68) -- the
 // variance is the mean of per-group biased variances, not the pooled variance.
 //
-// forward : (1) partial sums per group in fp64 atomics, (2) one tiny finalize CTA turning sums into the
-//           applied {mean, inv_std} per group, (3) streaming apply y = (x - mean) * inv_std.
-// backward: same three steps with sum(g), sum(g*x): the reference does not detach the statistics, so
+// forward : (1) partial sums per group (128-bit loads, fp64 atomics); the LAST CTA to finish (ticket counter in the
+//           workspace) turns the sums into the applied {mean, inv_std} per group, (2) streaming apply
+//           y = (x - mean) * inv_std.  Two launches; the second read of x comes out of the 126 MB L2.
+// backward: same two steps with sum(g), sum(g*x): the reference does not detach the statistics, so
 //           d x_i = g_i*r + A + Bc*(x_i - mu_group(i)).
 //
 // Workspace layout (floats, caller-owned; NG = T*B*G groups, G = 1 or C):
 //   stats: [0, 4NG)  2NG doubles  sum(x), sum(x^2) per group           (fwd scratch)
 //          [4NG,6NG) {mean, var} per group
 //          [6NG,8NG) {mean_applied, inv_std_applied} per group
+//          [8NG]     ticket counter of the sums kernel (unsigned)
 //   red  : [0, 4NG)  2NG doubles  sum(g), sum(g*x) per group           (bwd scratch)
 //          [4NG,7NG) {r', A, Bc} per group
+//          [7NG]     ticket counter
 #include "common.cuh"
 
 namespace {
@@ -29,28 +32,8 @@ struct PtrPack {
   float* out[MAX_T];
 };
 
-// grid: (chunks, NG).  Group gidx = (t*B + b)*G + gc covers `glen` contiguous floats.
-__global__ void __launch_bounds__(NT)
-group_sums_kernel(PtrPack pk, int B, int G, size_t glen, double* __restrict__ sums, bool with_second) {
-  const int gidx = blockIdx.y;
-  const int t = gidx / (B * G), rem = gidx - t * (B * G);
-  const float* x = pk.in[t] + (size_t)rem * glen;
-  const float* w = with_second ? pk.in2[t] + (size_t)rem * glen : nullptr;
-  // fwd: s0 = sum x, s1 = sum x^2 ; bwd (with_second: x = grad, w = input): s0 = sum g, s1 = sum g*x
-  float acc[2] = {0.f, 0.f};
-  const size_t per = (glen + gridDim.x - 1) / gridDim.x;
-  const size_t lo = (size_t)blockIdx.x * per, hi = min(glen, lo + per);
-  for (size_t i = lo + threadIdx.x; i < hi; i += NT) {
-    const float a = x[i];
-    const float bb = with_second ? w[i] : a;
-    acc[0] += a;
-    acc[1] = fmaf(a, bb, acc[1]);
-  }
-  ocf_block_accumulate<2>(acc, sums + 2 * (size_t)gidx);
-}
-
-__global__ void norm_finalize_fwd_kernel(float* __restrict__ stats, int NG, double inv_len, int flags) {
-  const double* sums = reinterpret_cast<const double*>(stats);
+__device__ __forceinline__ void finalize_fwd(float* __restrict__ stats, int NG, double inv_len, int flags) {
+  const volatile double* sums = reinterpret_cast<const volatile double*>(stats);  // written by other CTAs' atomics
   float* grp = stats + 4 * (size_t)NG;
   float* app = stats + 6 * (size_t)NG;
   __shared__ double sm[2];
@@ -78,29 +61,8 @@ __global__ void norm_finalize_fwd_kernel(float* __restrict__ stats, int NG, doub
   }
 }
 
-// y = (x - m) * r per group.  grid: (chunks, NG)
-__global__ void __launch_bounds__(NT)
-norm_apply_kernel(PtrPack pk, int B, int G, size_t glen, const float* __restrict__ app, bool vec) {
-  const int gidx = blockIdx.y;
-  const int t = gidx / (B * G), rem = gidx - t * (B * G);
-  const float* x = pk.in[t] + (size_t)rem * glen;
-  float* y = pk.out[t] + (size_t)rem * glen;
-  const float m = app[2 * gidx], r = app[2 * gidx + 1];
-  if (vec) {
-    const size_t n4 = glen / 4;
-    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < n4; i += (size_t)gridDim.x * NT) {
-      float4 v = reinterpret_cast<const float4*>(x)[i];
-      v.x = (v.x - m) * r; v.y = (v.y - m) * r; v.z = (v.z - m) * r; v.w = (v.w - m) * r;
-      reinterpret_cast<float4*>(y)[i] = v;
-    }
-  } else {
-    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < glen; i += (size_t)gridDim.x * NT) y[i] = (x[i] - m) * r;
-  }
-}
-
-__global__ void norm_finalize_bwd_kernel(const float* __restrict__ stats, float* __restrict__ red, int NG, double glen, int flags) {
-  const double* sums = reinterpret_cast<const double*>(red);  // sum g, sum g*x per group
-  const float* grp = stats + 4 * (size_t)NG;
+__device__ __forceinline__ void finalize_bwd(const float* __restrict__ stats, float* __restrict__ red, int NG, double glen, int flags) {
+  const volatile double* sums = reinterpret_cast<const volatile double*>(red);  // sum g, sum g*x per group
   const float* app = stats + 6 * (size_t)NG;
   float* co = red + 4 * (size_t)NG;
   const bool across = flags & OCF_NORM_ACROSS_IMAGES, nz = flags & OCF_NORM_NORMALIZE, ce = flags & OCF_NORM_CENTER;
@@ -124,11 +86,90 @@ __global__ void norm_finalize_bwd_kernel(const float* __restrict__ stats, float*
     co[3 * g + 1] = (float)(dLdm / cnt);
     co[3 * g + 2] = (float)(dLdv * 2.0 / cnt);                  // multiplies (x_i - mu_group(i))
   }
-  (void)grp;
+}
+
+// grid: (chunks, NG).  Group gidx = (t*B + b)*G + gc covers `glen` contiguous floats.
+// fwd: s0 = sum x, s1 = sum x^2 ; bwd (SECOND: x = grad, w = input): s0 = sum g, s1 = sum g*x.
+// The last CTA (ticket) runs the finalize step, so no separate launch is needed between the sums and the apply pass.
+template <bool SECOND, bool VEC>
+__global__ void __launch_bounds__(NT)
+group_sums_kernel(PtrPack pk, int B, int G, size_t glen, float* __restrict__ ws, unsigned* __restrict__ ticket,
+                  const float* __restrict__ stats_for_bwd, int NG, int flags) {
+  const int gidx = blockIdx.y;
+  const int t = gidx / (B * G), rem = gidx - t * (B * G);
+  const float* x = pk.in[t] + (size_t)rem * glen;
+  const float* w = SECOND ? pk.in2[t] + (size_t)rem * glen : nullptr;
+  float acc[2] = {0.f, 0.f};
+  if (VEC) {
+    const size_t n4 = glen / 4;
+    const size_t per = (n4 + gridDim.x - 1) / gridDim.x;
+    const size_t lo = (size_t)blockIdx.x * per, hi = min(n4, lo + per);
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;  // two independent chains per sum
+    size_t i = lo + threadIdx.x;
+    for (; i + NT < hi; i += 2 * NT) {
+      const float4 u = ocf_ldg_stream4(x + 4 * i), v = ocf_ldg_stream4(x + 4 * (i + NT));
+      float4 p = u, q = v;
+      if (SECOND) { p = ocf_ldg_stream4(w + 4 * i); q = ocf_ldg_stream4(w + 4 * (i + NT)); }
+      a0 += (u.x + u.y) + (u.z + u.w);
+      a1 += (v.x + v.y) + (v.z + v.w);
+      b0 = fmaf(u.x, p.x, fmaf(u.y, p.y, fmaf(u.z, p.z, fmaf(u.w, p.w, b0))));
+      b1 = fmaf(v.x, q.x, fmaf(v.y, q.y, fmaf(v.z, q.z, fmaf(v.w, q.w, b1))));
+    }
+    if (i < hi) {
+      const float4 u = ocf_ldg_stream4(x + 4 * i);
+      float4 p = u;
+      if (SECOND) p = ocf_ldg_stream4(w + 4 * i);
+      a0 += (u.x + u.y) + (u.z + u.w);
+      b0 = fmaf(u.x, p.x, fmaf(u.y, p.y, fmaf(u.z, p.z, fmaf(u.w, p.w, b0))));
+    }
+    acc[0] = a0 + a1;
+    acc[1] = b0 + b1;
+  } else {
+    const size_t per = (glen + gridDim.x - 1) / gridDim.x;
+    const size_t lo = (size_t)blockIdx.x * per, hi = min(glen, lo + per);
+    for (size_t i = lo + threadIdx.x; i < hi; i += NT) {
+      const float a = x[i];
+      const float bb = SECOND ? w[i] : a;
+      acc[0] += a;
+      acc[1] = fmaf(a, bb, acc[1]);
+    }
+  }
+  ocf_block_accumulate<2>(acc, reinterpret_cast<double*>(ws) + 2 * (size_t)gidx);
+  // ---- last CTA finalises ----
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (SECOND) finalize_bwd(stats_for_bwd, ws, NG, (double)glen, flags);
+  else finalize_fwd(ws, NG, 1.0 / (double)glen, flags);
+}
+
+// y = (x - m) * r per group.  grid: (chunks, NG)
+__global__ void __launch_bounds__(NT)
+norm_apply_kernel(PtrPack pk, int B, int G, size_t glen, const float* __restrict__ app, bool vec) {
+  const int gidx = blockIdx.y;
+  const int t = gidx / (B * G), rem = gidx - t * (B * G);
+  const float* x = pk.in[t] + (size_t)rem * glen;
+  float* y = pk.out[t] + (size_t)rem * glen;
+  const float m = app[2 * gidx], r = app[2 * gidx + 1];
+  if (vec) {
+    const size_t n4 = glen / 4;
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < n4; i += (size_t)gridDim.x * NT) {
+      float4 v = reinterpret_cast<const float4*>(x)[i];
+      v.x = (v.x - m) * r; v.y = (v.y - m) * r; v.z = (v.z - m) * r; v.w = (v.w - m) * r;
+      reinterpret_cast<float4*>(y)[i] = v;
+    }
+  } else {
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < glen; i += (size_t)gridDim.x * NT) y[i] = (x[i] - m) * r;
+  }
 }
 
 __global__ void __launch_bounds__(NT)
-norm_bwd_apply_kernel(PtrPack pk, int B, int G, size_t glen, const float* __restrict__ stats, const float* __restrict__ red, int NG) {
+norm_bwd_apply_kernel(PtrPack pk, int B, int G, size_t glen, const float* __restrict__ stats, const float* __restrict__ red, int NG,
+                      bool vec) {
   const int gidx = blockIdx.y;
   const int t = gidx / (B * G), rem = gidx - t * (B * G);
   const float* g = pk.in[t] + (size_t)rem * glen;
@@ -137,8 +178,19 @@ norm_bwd_apply_kernel(PtrPack pk, int B, int G, size_t glen, const float* __rest
   const float mu = stats[4 * (size_t)NG + 2 * gidx];
   const float* co = red + 4 * (size_t)NG + 3 * (size_t)gidx;
   const float r = co[0], A = co[1], Bc = co[2];
-  for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < glen; i += (size_t)gridDim.x * NT)
-    dx[i] = fmaf(g[i], r, fmaf(Bc, x[i] - mu, A));
+  if (vec) {
+    const size_t n4 = glen / 4;
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < n4; i += (size_t)gridDim.x * NT) {
+      const float4 gv = ocf_ldg_stream4(g + 4 * i), xv = ocf_ldg_stream4(x + 4 * i);
+      float4 o;
+      o.x = fmaf(gv.x, r, fmaf(Bc, xv.x - mu, A)); o.y = fmaf(gv.y, r, fmaf(Bc, xv.y - mu, A));
+      o.z = fmaf(gv.z, r, fmaf(Bc, xv.z - mu, A)); o.w = fmaf(gv.w, r, fmaf(Bc, xv.w - mu, A));
+      reinterpret_cast<float4*>(dx)[i] = o;
+    }
+  } else {
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < glen; i += (size_t)gridDim.x * NT)
+      dx[i] = fmaf(g[i], r, fmaf(Bc, x[i] - mu, A));
+  }
 }
 
 int chunks_for(size_t glen, int NG) {
@@ -174,12 +226,12 @@ extern "C" int ocf_normalize_fwd(const float* const* xs, float* const* ys, int T
   const int NG = (int)NGll;
   vec = vec && (glen % 4 == 0);
   cudaStream_t s = ocf_cast_stream(stream);
-  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * NG, s);
+  unsigned* ticket = reinterpret_cast<unsigned*>(stats + 8 * (size_t)NG);
+  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(float) * (8 * (size_t)NG + 2), s);  // fp64 sums and the ticket in one go
   if (e != cudaSuccess) return (int)e;
   const int chunks = chunks_for(glen, NG);
-  group_sums_kernel<<<dim3(chunks, NG), NT, 0, s>>>(pk, B, G, glen, reinterpret_cast<double*>(stats), false);
-  if (int st = ocf_launch_status()) return st;
-  norm_finalize_fwd_kernel<<<1, 256, 0, s>>>(stats, NG, 1.0 / (double)glen, flags);
+  if (vec) group_sums_kernel<false, true><<<dim3(chunks, NG), NT, 0, s>>>(pk, B, G, glen, stats, ticket, nullptr, NG, flags);
+  else group_sums_kernel<false, false><<<dim3(chunks, NG), NT, 0, s>>>(pk, B, G, glen, stats, ticket, nullptr, NG, flags);
   if (int st = ocf_launch_status()) return st;
   norm_apply_kernel<<<dim3(chunks, NG), NT, 0, s>>>(pk, B, G, glen, stats + 6 * (size_t)NG, vec);
   return ocf_launch_status();
@@ -193,9 +245,11 @@ extern "C" int ocf_normalize_bwd(const float* const* grad_ys, const float* const
   OCF_REQUIRE((flags & ~15) == 0, OCF_EUNSUPPORTED);
   OCF_REQUIRE((reinterpret_cast<uintptr_t>(red) & 7u) == 0, OCF_EALIGN);
   PtrPack pk;
+  bool vec = true;
   for (int t = 0; t < T; ++t) {
     OCF_REQUIRE_PTR(grad_ys[t]); OCF_REQUIRE_PTR(xs[t]); OCF_REQUIRE_PTR(grad_xs[t]);
     pk.in[t] = grad_ys[t]; pk.in2[t] = xs[t]; pk.out[t] = grad_xs[t];
+    vec = vec && ocf_aligned16(grad_ys[t]) && ocf_aligned16(xs[t]) && ocf_aligned16(grad_xs[t]);
   }
   const int G = (flags & OCF_NORM_ACROSS_CHANNELS) ? 1 : C;
   const size_t glen = (size_t)(G == 1 ? C : 1) * H * W;
@@ -203,13 +257,14 @@ extern "C" int ocf_normalize_bwd(const float* const* grad_ys, const float* const
   OCF_REQUIRE(NGll <= 65535, OCF_EUNSUPPORTED);
   const int NG = (int)NGll;
   cudaStream_t s = ocf_cast_stream(stream);
-  cudaError_t e = cudaMemsetAsync(red, 0, sizeof(double) * 2 * NG, s);
+  vec = vec && (glen % 4 == 0);
+  unsigned* ticket = reinterpret_cast<unsigned*>(red + 7 * (size_t)NG);
+  cudaError_t e = cudaMemsetAsync(red, 0, sizeof(float) * (8 * (size_t)NG), s);  // fp64 sums and the ticket in one go
   if (e != cudaSuccess) return (int)e;
   const int chunks = chunks_for(glen, NG);
-  group_sums_kernel<<<dim3(chunks, NG), NT, 0, s>>>(pk, B, G, glen, reinterpret_cast<double*>(red), true);
+  if (vec) group_sums_kernel<true, true><<<dim3(chunks, NG), NT, 0, s>>>(pk, B, G, glen, red, ticket, stats, NG, flags);
+  else group_sums_kernel<true, false><<<dim3(chunks, NG), NT, 0, s>>>(pk, B, G, glen, red, ticket, stats, NG, flags);
   if (int st = ocf_launch_status()) return st;
-  norm_finalize_bwd_kernel<<<1, 256, 0, s>>>(stats, red, NG, (double)glen, flags);
-  if (int st = ocf_launch_status()) return st;
-  norm_bwd_apply_kernel<<<dim3(chunks, NG), NT, 0, s>>>(pk, B, G, glen, stats, red, NG);
+  norm_bwd_apply_kernel<<<dim3(chunks, NG), NT, 0, s>>>(pk, B, G, glen, stats, red, NG, vec);
   return ocf_launch_status();
 }

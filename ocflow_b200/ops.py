@@ -103,7 +103,7 @@ class _Normalize(torch.autograd.Function):
         G = 1 if flags & NORM_ACROSS_CHANNELS else C
         NG = T * B * G
         ys = [torch.empty_like(x) for x in xs]
-        stats = torch.empty(8 * NG, device=xs[0].device, dtype=torch.float32)
+        stats = torch.empty(8 * NG + 8, device=xs[0].device, dtype=torch.float32)
         with torch.cuda.device_of(xs[0]):
             _lib.call("ocf_normalize_fwd", ctypes.cast(_ptr_array(xs), ctypes.c_void_p), ctypes.cast(_ptr_array(ys), ctypes.c_void_p),
                       T, B, C, H, W, flags, _p(stats), _stream())
