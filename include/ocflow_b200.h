@@ -182,6 +182,21 @@ int ocf_pair_loss(const float* a, const float* b, double* sum_out, float* grad, 
                   ocf_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * SSIM.  Replaces _ssim / ssim / SSIM.forward of inpainting_metrics/ssim/ssim.py:7-75 (the only "SSIM-style" term the
+ *   reference defines): window x window Gaussian (sigma 1.5), zero padding window//2, C1 = 0.01^2, C2 = 0.03^2,
+ *   depthwise over the C channels.  The map has Ho x Wo = (H + 2*(window/2) - window + 1) x (...) pixels per channel
+ *   ((H+1) x (W+1) for even windows, as F.conv2d gives).  window <= 15.
+ *   sums: B doubles, the sum of the map per batch item (mean = sums[b] / (C*Ho*Wo); the reference's size_average
+ *   variants are both derived from it).
+ *   coef: optional workspace of 4*B*C*Ho*Wo floats receiving the per-pixel partial derivatives for ocf_ssim_bwd.
+ * ------------------------------------------------------------------------------------------- */
+int ocf_ssim_fwd(const float* img1, const float* img2, double* sums, float* coef, int B, int C, int H, int W,
+                 int window, ocf_stream_t stream);
+/* d_img1 / d_img2 (either may be NULL) = scale[b] * d(sums[b]) / d img;  scale: B floats on the device. */
+int ocf_ssim_bwd(const float* img1, const float* img2, const float* coef, const float* scale, float* d_img1,
+                 float* d_img2, int B, int C, int H, int W, int window, ocf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host-buffer convenience entry points (HOST pointers; allocate, copy in, run, copy out, free,
  * synchronise).  They exist so the C ABI can be exercised end-to-end without any Python/torch.
  * ------------------------------------------------------------------------------------------- */

@@ -60,3 +60,26 @@ def occlusion_bce_loss(occ_pred, occ):
 def occlusion_focal_loss(occ_pred, occ):
     """Focal BCE (gamma=2) of OcclusionModel.general_step (models/occlusion_model.py:55-62)."""
     return ops.pair_loss(occ_pred, occ, ops.PAIR_FOCAL)
+
+
+def ssim(img1, img2, window_size=11, size_average=True):
+    """inpainting_metrics/ssim/ssim.py:64-75 (`ssim`): mean of the SSIM map (or per-item means when size_average=False)."""
+    return ops.ssim(img1, img2, window_size, size_average)
+
+
+class SSIM(nn.Module):
+    """inpainting_metrics/ssim/ssim.py:39-62 (`SSIM` module; the cached window of the reference is internal to the kernel)."""
+
+    def __init__(self, window_size=11, size_average=True):
+        super().__init__()
+        self.window_size = window_size
+        self.size_average = size_average
+
+    def forward(self, img1, img2):
+        return ops.ssim(img1, img2, self.window_size, self.size_average)
+
+
+def ssim_photometric_loss(img_pred, img, window_size=11):
+    """SSIM-style photometric term named by north_star: (1 - SSIM(img_pred, img)) / 2, differentiable in both images.
+    The reference defines SSIM only as a metric; this is the standard loss form built on its exact definition."""
+    return (1.0 - ops.ssim(img_pred, img, window_size, True)) * 0.5

@@ -407,6 +407,51 @@ def pair_loss(a, b, kind):
 
 
 # -------------------------------------------------------------------------------------------------
+# SSIM (inpainting_metrics/ssim/ssim.py)
+# -------------------------------------------------------------------------------------------------
+class _SSIM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img1, img2, window, size_average):
+        B, C, H, W = img1.shape
+        Ho, Wo = H + 2 * (window // 2) - window + 1, W + 2 * (window // 2) - window + 1
+        sums = torch.empty(B, device=img1.device, dtype=torch.float64)
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        coef = torch.empty((B, C, 4, Ho, Wo), device=img1.device, dtype=torch.float32) if need else None
+        with torch.cuda.device_of(img1):
+            _lib.call("ocf_ssim_fwd", _p(img1), _p(img2), _p(sums), _p(coef), B, C, H, W, window, _stream())
+        ctx.window, ctx.size_average, ctx.numel = window, size_average, C * Ho * Wo
+        if need:
+            ctx.save_for_backward(img1, img2, coef)
+        per_item = sums / float(C * Ho * Wo)
+        # ssim_map.mean() == mean over items of the per-item means (all items have the same number of elements)
+        return (per_item.mean() if size_average else per_item).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        img1, img2, coef = ctx.saved_tensors
+        B, C, H, W = img1.shape
+        if ctx.size_average:
+            scale = (g.to(torch.float32) / float(B * ctx.numel)).expand(B).contiguous()
+        else:
+            scale = (g.to(torch.float32) / float(ctx.numel)).contiguous()
+        d1 = torch.empty_like(img1) if ctx.needs_input_grad[0] else None
+        d2 = torch.empty_like(img2) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device_of(img1):
+            _lib.call("ocf_ssim_bwd", _p(img1), _p(img2), _p(coef), _p(scale), _p(d1), _p(d2), B, C, H, W, ctx.window, _stream())
+        return d1, d2, None, None
+
+
+def ssim(img1, img2, window_size=11, size_average=True):
+    img1 = _req(img1, "img1", 4)
+    img2 = _req(img2, "img2", 4)
+    if img1.shape != img2.shape:
+        raise ValueError("img1 and img2 must have the same shape")
+    if not 1 <= int(window_size) <= 15:
+        raise ValueError("window_size must be in [1, 15] (got %d)" % window_size)
+    return _SSIM.apply(img1, img2, int(window_size), bool(size_average))
+
+
+# -------------------------------------------------------------------------------------------------
 # fused occlusion-aware photometric pass (models/model.py:379-407 in one kernel)
 # -------------------------------------------------------------------------------------------------
 class _OccPhotoFused(torch.autograd.Function):

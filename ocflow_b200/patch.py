@@ -91,6 +91,13 @@ def patch_reference(verbose=False):
     if ut is not None and hasattr(ut, "charbonnier_loss"):
         setp(ut, "warp", warping.warp)
         setp(ut, "charbonnier_loss", losses.charbonnier_loss)
+    # SSIM (inpainting_metrics/ssim/ssim.py:39-75): the functional entry point and the module
+    sm = _try_import("inpainting_metrics.ssim.ssim")
+    setp(sm, "ssim", losses.ssim)
+    setp(sm, "SSIM", losses.SSIM)
+    pkg = _try_import("inpainting_metrics.ssim")
+    setp(pkg, "ssim", losses.ssim)
+    setp(pkg, "SSIM", losses.SSIM)
     if verbose:
         for d in done:
             print("patched", d)

@@ -241,3 +241,28 @@ def test_corr_backward_consumes_concat_gradient_slice_in_place(shape):
     want = run(lambda a, b: torch.nn.functional.leaky_relu(O.cost_volume(a, b, 4), 0.1), "cpu")
     for m, w in zip(mine, want):
         assert_close(m, w, TOL, "corr grad through a concat slice")
+
+
+@pytest.mark.parametrize("shape,ws", [((2, 3, 37, 45), 11), ((1, 3, 16, 16), 11), ((2, 3, 21, 18), 4), ((1, 1, 9, 70), 7),
+                                      ((2, 3, 64, 96), 11)])
+def test_ssim_matches_oracle_value_and_gradients(shape, ws):
+    """inpainting_metrics/ssim/ssim.py:17-37.  The oracle's ssim is pinned to the real reference by the golden fixtures
+    (tests/test_oracle_golden.py: ref_ssim11, ref_ssim4_map_mean); here the CUDA kernel meets it, both reductions."""
+    import ocflow_b200 as ocf
+
+    g = torch.Generator().manual_seed(5)
+    i1 = torch.rand(*shape, generator=g)
+    i2 = (i1 + 0.2 * torch.randn(*shape, generator=g)).clamp(0, 1)
+    for size_average in (True, False):
+        a, b = i1.clone().requires_grad_(True), i2.clone().requires_grad_(True)
+        want = O.ssim(a, b, ws, size_average)
+        cot = torch.ones_like(want) if size_average else torch.linspace(0.5, 1.5, shape[0])
+        (want * cot).sum().backward()
+        ac, bc = i1.clone().cuda().requires_grad_(True), i2.clone().cuda().requires_grad_(True)
+        mine = ocf.ssim(ac, bc, ws, size_average)
+        (mine * cot.cuda()).sum().backward()
+        assert_close(mine.reshape(-1), want.reshape(-1), LOSS_TOL, "ssim ws=%d" % ws)
+        assert_close(ac.grad, a.grad, 2e-4, "d ssim / d img1")
+        assert_close(bc.grad, b.grad, 2e-4, "d ssim / d img2")
+    loss = ocf.ssim_photometric_loss(i1.cuda(), i2.cuda(), ws)
+    assert_scalar_close(loss, (1 - O.ssim(i1, i2, ws)) / 2, LOSS_TOL)
