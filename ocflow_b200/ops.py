@@ -84,6 +84,15 @@ def cost_volume(f1, f2, max_displacement=4, leaky_slope=1.0):
     f2 = _req(f2, "features2", 4)
     if f1.shape != f2.shape:
         raise ValueError("features1 and features2 must have the same shape (got %s vs %s)" % (tuple(f1.shape), tuple(f2.shape)))
+    W = f1.shape[3]
+    if W % 4 != 0 and int(max_displacement) == 4 and W >= 16:
+        # Ragged rows (KITTI / Sintel pyramids: 621, 311, 39 ...) cannot be described to the TMA unit (global strides must be
+        # multiples of 16 bytes).  Zero columns on the right are exactly the reference's out-of-image zeros, so the rows are
+        # re-pitched to a multiple of 4 and the regular kernels run; autograd slices / pads the gradients the same way.
+        pad = (-W) % 4
+        out = _CostVolume.apply(torch.nn.functional.pad(f1, (0, pad)), torch.nn.functional.pad(f2, (0, pad)),
+                                int(max_displacement), float(leaky_slope))
+        return out[..., :W]
     return _CostVolume.apply(f1, f2, int(max_displacement), float(leaky_slope))
 
 

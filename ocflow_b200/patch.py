@@ -95,9 +95,6 @@ def patch_reference(verbose=False):
     sm = _try_import("inpainting_metrics.ssim.ssim")
     setp(sm, "ssim", losses.ssim)
     setp(sm, "SSIM", losses.SSIM)
-    pkg = _try_import("inpainting_metrics.ssim")
-    setp(pkg, "ssim", losses.ssim)
-    setp(pkg, "SSIM", losses.SSIM)
     if verbose:
         for d in done:
             print("patched", d)
