@@ -197,6 +197,21 @@ int ocf_ssim_bwd(const float* img1, const float* img2, const float* coef, const 
                  float* d_img2, int B, int C, int H, int W, int window, ocf_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Soft census (ternary) photometric term.  north_star lists a census term; the reference defines NONE (SURVEY.md section
+ *   8a-14), so there is no reference interface to cite: PARITY UNPINNED, the semantics are those of
+ *   oracle/ocflow_oracle.py::census_loss (UnFlow soft census: grey*255, (2m+1)^2 patch, t = u/sqrt(0.81+u^2), soft Hamming
+ *   dt^2/(0.1+dt^2) averaged over the patch, m-pixel border masked) with the occlusion weighting of photometric_error
+ *   (models/model.py:37-46).  max_distance m in 1..3.
+ *   sums (2 doubles, device, zeroed inside): [0] sum dist*w, [1] sum w, w = interior * (1 - occ); occ may be NULL.
+ *   The host forms sums[0] / (sums[1] + 1e-16).
+ * ------------------------------------------------------------------------------------------- */
+int ocf_census_fwd(const float* pred, const float* img, const float* occ, double* sums, int B, int C, int H, int W,
+                   int max_distance, ocf_stream_t stream);
+/* d_pred = coef[0] * d sums[0] / d pred  (coef: 1 float on the device; img is data, occ is computed under no_grad). */
+int ocf_census_bwd(const float* pred, const float* img, const float* occ, const float* coef, float* d_pred, int B, int C,
+                   int H, int W, int max_distance, ocf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host-buffer convenience entry points (HOST pointers; allocate, copy in, run, copy out, free,
  * synchronise).  They exist so the C ABI can be exercised end-to-end without any Python/torch.
  * ------------------------------------------------------------------------------------------- */

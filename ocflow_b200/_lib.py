@@ -38,6 +38,8 @@ SIGNATURES = {
     "ocf_pair_loss": [c_f, c_f, c_f, c_f, c_ll, c_i, c_s],
     "ocf_ssim_fwd": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_s],
     "ocf_ssim_bwd": [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_s],
+    "ocf_census_fwd": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_s],
+    "ocf_census_bwd": [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_s],
     "ocf_host_corr_fwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i],
     "ocf_host_warp_fwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i],
     "ocf_host_range_map": [c_f, c_f, c_i, c_i, c_i],
@@ -81,14 +83,28 @@ KERNELS_PER_CALL = {
     "ocf_corr_fwd": 1, "ocf_corr_bwd": 1, "ocf_normalize_fwd": 2, "ocf_normalize_bwd": 2, "ocf_warp_fwd": 1,
     "ocf_warp_bwd": 1, "ocf_range_map": 1, "ocf_flow_to_warp": 1, "ocf_robust_l1_fwd": 1, "ocf_robust_l1_bwd": 1,
     "ocf_photometric_fwd": 1, "ocf_photometric_bwd": 1, "ocf_smooth_fwd": 1, "ocf_smooth_bwd": 1, "ocf_gradient": 1,
-    "ocf_occ_photo_fused": 1, "ocf_pair_loss": 1, "ocf_ssim_fwd": 1, "ocf_ssim_bwd": 1,
+    "ocf_occ_photo_fused": 1, "ocf_pair_loss": 1, "ocf_ssim_fwd": 1, "ocf_ssim_bwd": 1, "ocf_census_fwd": 1, "ocf_census_bwd": 1,
 }
+
+
+# optional live timer (bench.py): when set to a list, every call is bracketed by CUDA events recorded on the stream the
+# kernels are enqueued on (torch's current stream == the stream argument); entries are (name, int_args, start, end).
+live_timer = None
 
 
 def call(name, *args):
     """Invoke an entry point; raise RuntimeError with the library's message on a non-zero status."""
     global launch_count
-    code = getattr(load(), name)(*args)
+    if live_timer is not None:
+        import torch
+
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        code = getattr(load(), name)(*args)
+        e1.record()
+        live_timer.append((name, tuple(a for a in args if isinstance(a, int)), e0, e1))
+    else:
+        code = getattr(load(), name)(*args)
     if code != 0:
         raise RuntimeError("ocflow_b200.%s failed: %s (code %d)" % (name, error_string(code), code))
     launch_count += KERNELS_PER_CALL.get(name, 0)

@@ -891,10 +891,15 @@ int set_smem(K kernel, size_t bytes) {
   return 0;
 }
 
-// Channel split factor (power of two <= 8).  Cost model in units of one full-tile CTA: ceil(tiles*ks / slots) rounds of
-// 1/ks tile each, plus a fixed allowance for the DSMEM reduction when ks > 1; at least `min_ch` channels per CTA.
-int pick_ksplit(long long tiles, int C, int min_ch, bool reduce_cost = true) {
-  if (const char* e = getenv(reduce_cost ? "OCF_KSPLIT_FWD" : "OCF_KSPLIT_BWD")) {  // developer override for tuning runs
+// Channel split factor (power of two <= 8), from a rounds-of-work cost model in units of "one channel of one tile":
+//   cost(ks) = ceil(tiles * ks / slots) * (prologue + C / ks) + (ks > 1 ? reduce : 0)
+// `prologue` is the fixed per-CTA cost expressed in channels.  Forward: the first TMA box (~4 channels) and, when split,
+// the DSMEM reduction of the 81 partial planes (~0.6 of a full tile).  Backward: staging + lifting the 81 coefficient
+// planes of the tile (and the LeakyReLU mask planes) costs as much as ~30 (16 without the mask) channels of the main
+// loop (measured: t(C) = 11 us + 0.36 us * C per round at the L2 geometry, tools/probe_corr.py), so splitting the
+// channels of an already full grid only multiplies that prologue.  At least `min_ch` channels per CTA.
+int pick_ksplit(long long tiles, int C, int min_ch, bool fwd, double prologue) {
+  if (const char* e = getenv(fwd ? "OCF_KSPLIT_FWD" : "OCF_KSPLIT_BWD")) {  // developer override for tuning runs
     const int v = atoi(e);
     if (v == 1 || v == 2 || v == 4 || v == 8) return v;
   }
@@ -904,7 +909,8 @@ int pick_ksplit(long long tiles, int C, int min_ch, bool reduce_cost = true) {
   for (int ks = 1; ks <= 8; ks *= 2) {
     if (ks > 1 && C / ks < min_ch) break;
     const long long rounds = (tiles * ks + slots - 1) / slots;
-    const double cost = (double)rounds / ks + ((ks > 1 && reduce_cost) ? 0.6 : 0.02 * (ks > 1));
+    const double per_cta = prologue + (double)((C + ks - 1) / ks);
+    const double cost = (double)rounds * per_cta + ((ks > 1 && fwd) ? 0.6 * C : 0.0);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = ks; }
   }
   return best;
@@ -974,7 +980,8 @@ extern "C" int ocf_corr_fwd(const float* f1, const float* f2, float* out, int B,
     using T = Tile4;
     const size_t smem = sizeof(float) * T::STAGES * (T::F1_STAGE + T::F2_STAGE);
     const int gx = (W + T::TW - 1) / T::TW, gy = (H + T::TH - 1) / T::TH;
-    const int ks = pick_ksplit((long long)gx * gy * B, C, 2 * T::CC);
+    // one tile or more per SM: the persistent kernel (ks == 1) keeps every SM busy without any reduction
+    const int ks = (long long)gx * gy * B >= OCF_SM_COUNT ? 1 : pick_ksplit((long long)gx * gy * B, C, 2 * T::CC, true, 4.0);
     dim3 grid(gx, gy, B * ks);
     const bool vec = (W % 4 == 0) && ocf_aligned16(f1) && ocf_aligned16(f2) && ocf_aligned16(out) && (out_bstride % 4 == 0);
     CUtensorMap m1, m2;
@@ -1024,7 +1031,7 @@ extern "C" int ocf_corr_bwd(const float* grad_out, const float* out_act, const f
     const int nmodes = (df1 != nullptr && df2 != nullptr) ? 2 : 1;
     const int first = df1 != nullptr ? 0 : 1;
     const int gx = (W + T::TW - 1) / T::TW, gy = (H + T::TH - 1) / T::TH;
-    const int ks = pick_ksplit((long long)gx * gy * B * nmodes, C, 2 * T::CC, false);
+    const int ks = pick_ksplit((long long)gx * gy * B * nmodes, C, 2 * T::CC, false, out_act != nullptr ? 30.0 : 16.0);
     dim3 grid(gx, gy, B * nmodes * ks);
     const bool vec = (W % 4 == 0) && ocf_aligned16(f1) && ocf_aligned16(f2) && (df1 == nullptr || ocf_aligned16(df1)) &&
                      (df2 == nullptr || ocf_aligned16(df2));

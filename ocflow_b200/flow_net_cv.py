@@ -87,11 +87,16 @@ class FlowNetCV(nn.Module):
         flow = getattr(self, "predict_flow%d" % lvl)(x)
         return x, flow
 
-    def forward(self, x):
-        if x.dim() != 4 or x.shape[1] != 6:
-            raise ValueError("FlowNetCV expects [B,6,H,W] (two RGB images), got %s" % (tuple(x.shape),))
-        p1 = self.pyramid(x[:, :3])
-        p2 = self.pyramid(x[:, 3:])
+    def pyramids(self, x):
+        """Feature pyramids of both images with ONE pass of the (weight-shared) encoder over a 2B batch: the reference runs
+        the same 18 convolutions twice (cost_volume_flow_net.py:158-169); per-sample results are identical."""
+        B, _, H, W = x.shape
+        both = x.reshape(B, 2, 3, H, W).transpose(0, 1).reshape(2 * B, 3, H, W)
+        feats = self.pyramid(both)
+        return {l: f[:B] for l, f in feats.items()}, {l: f[B:] for l, f in feats.items()}
+
+    def decode(self, p1, p2):
+        """Coarse-to-fine decoder of cost_volume_flow_net.py:171-246 on two given pyramids."""
         up_flow = up_feat = None
         for lvl in (6, 5, 4, 3, 2):
             feat, flow = self._level(lvl, p1[lvl], p2[lvl], up_flow, up_feat)
@@ -104,3 +109,22 @@ class FlowNetCV(nn.Module):
         flow2 = flow + self.dc_conv7(t)
         flow1 = F.interpolate(flow2, scale_factor=4, mode="bilinear", align_corners=True) * 20
         return flow1, flow2 * 5.0
+
+    def forward(self, x):
+        if x.dim() != 4 or x.shape[1] != 6:
+            raise ValueError("FlowNetCV expects [B,6,H,W] (two RGB images), got %s" % (tuple(x.shape),))
+        p1, p2 = self.pyramids(x)
+        return self.decode(p1, p2)
+
+    def forward_bidirectional(self, x):
+        """(flow1, flow_l2) of forward(x) plus the no-grad full-resolution flow of the swapped pair, i.e. what
+        models/model.py:380-386 obtains from `self(imgs)` and `self(cat(img2, img1))`.  The swapped evaluation needs the
+        pyramids of the same two images (its c1 pyramid is this call's c2 pyramid and vice versa), so the encoder runs once
+        instead of twice more; normalize_features statistics stay per evaluation."""
+        if x.dim() != 4 or x.shape[1] != 6:
+            raise ValueError("FlowNetCV expects [B,6,H,W] (two RGB images), got %s" % (tuple(x.shape),))
+        p1, p2 = self.pyramids(x)
+        flow1, flow_l2 = self.decode(p1, p2)
+        with torch.no_grad():
+            back_flow1, _ = self.decode({l: f.detach() for l, f in p2.items()}, {l: f.detach() for l, f in p1.items()})
+        return flow1, flow_l2, back_flow1

@@ -29,6 +29,8 @@ class FlowStageModel(nn.Module):
         self.log_every_n_steps = hparams.get("log_every_n_steps", 20)
         self.occ_aware = hparams.get("occ_aware", False)
         self.displacement = hparams.get("displacement", 4)
+        # not a reference hyper-parameter: False evaluates the network twice exactly as models/model.py:380-386 is written
+        self.share_encoder = hparams.get("share_encoder", True)
         model = hparams.get("model", "simple")
         self.model = model
         if model != "pwc":
@@ -95,9 +97,14 @@ class FlowStageModel(nn.Module):
     def general_step_occ_aware(self, batch, batch_idx, mode):
         imgs, flow, occ = self._unpack(batch)
         img1, img2 = imgs[:, 0:3], imgs[:, 3:6]
-        flow_pred, flow_l2 = self(imgs)
+        if self.share_encoder:
+            # same values as the two evaluations below; the swapped pair reuses this evaluation's feature pyramids
+            flow_pred, flow_l2, back_flow_pred = self.flow_pred.forward_bidirectional(imgs)
+        else:
+            flow_pred, flow_l2 = self(imgs)
+            with torch.no_grad():
+                back_flow_pred, _ = self(torch.cat((img2, img1), dim=1))
         with torch.no_grad():
-            back_flow_pred, _ = self(torch.cat((img2, img1), dim=1))
             range_map = ops.range_map(back_flow_pred)
         photo, photo_occ, flow_error, occ_error = ops.occ_photo_fused(img1, img2, flow_pred, range_map, flow, occ)
         smooth1, smooth2 = self._smoothness(img1, flow_l2)

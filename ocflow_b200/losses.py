@@ -83,3 +83,9 @@ def ssim_photometric_loss(img_pred, img, window_size=11):
     """SSIM-style photometric term named by north_star: (1 - SSIM(img_pred, img)) / 2, differentiable in both images.
     The reference defines SSIM only as a metric; this is the standard loss form built on its exact definition."""
     return (1.0 - ops.ssim(img_pred, img, window_size, True)) * 0.5
+
+
+def census_loss(img_pred, img, occ=None, max_distance=3):
+    """Census-style photometric term named by north_star.  The reference defines no census loss:
+    this is the published UnFlow soft census with the occlusion weighting of photometric_error -- parity unpinned."""
+    return ops.census_loss(img_pred, img, occ, max_distance)

@@ -461,6 +461,53 @@ def ssim(img1, img2, window_size=11, size_average=True):
 
 
 # -------------------------------------------------------------------------------------------------
+# soft census term (no reference definition: parity unpinned, oracle census_loss)
+# -------------------------------------------------------------------------------------------------
+class _Census(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, img, occ, max_distance):
+        B, C, H, W = pred.shape
+        sums = torch.empty(2, device=pred.device, dtype=torch.float64)
+        with torch.cuda.device_of(pred):
+            _lib.call("ocf_census_fwd", _p(pred), _p(img), _p(occ), _p(sums), B, C, H, W, max_distance, _stream())
+        den = sums[1] + 1e-16
+        ctx.m, ctx.has_occ = max_distance, occ is not None
+        if occ is not None:
+            ctx.save_for_backward(pred, img, den, occ)
+        else:
+            ctx.save_for_backward(pred, img, den)
+        return (sums[0] / den).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, img, den = ctx.saved_tensors[:3]
+        occ = ctx.saved_tensors[3] if ctx.has_occ else None
+        B, C, H, W = pred.shape
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None
+        coef = (g.to(torch.float64) / den).to(torch.float32).reshape(1).contiguous()
+        d_pred = torch.empty_like(pred)
+        with torch.cuda.device_of(pred):
+            _lib.call("ocf_census_bwd", _p(pred), _p(img), _p(occ), _p(coef), _p(d_pred), B, C, H, W, ctx.m, _stream())
+        return d_pred, None, None, None
+
+
+def census_loss(img_pred, img, occ=None, max_distance=3):
+    """Occlusion-weighted soft census distance between img_pred and img (gradient flows to img_pred only)."""
+    pred = _req(img_pred, "img_pred", 4)
+    img = _req(img.detach(), "img", 4)
+    if pred.shape != img.shape:
+        raise ValueError("img_pred and img must have the same shape")
+    if occ is not None:
+        occ = _req(occ.detach(), "occ", 4)
+        if occ.shape != (pred.shape[0], 1, pred.shape[2], pred.shape[3]):
+            raise ValueError("occ must be [B,1,H,W]")
+    if not 1 <= int(max_distance) <= 3:
+        raise ValueError("max_distance must be 1, 2 or 3 (got %d)" % max_distance)
+    return _Census.apply(pred, img, occ, int(max_distance))
+
+
+# -------------------------------------------------------------------------------------------------
 # fused occlusion-aware photometric pass (models/model.py:379-407 in one kernel)
 # -------------------------------------------------------------------------------------------------
 class _OccPhotoFused(torch.autograd.Function):

@@ -288,6 +288,56 @@ def ssim(img1, img2, window_size=11, size_average=True):
 
 
 # --------------------------------------------------------------------------------------------
+# census (ternary) photometric term -- PARITY UNPINNED
+#   BASELINE.json's north_star names a census term, but the reference defines none (SURVEY.md section 8a-14:
+#   "census: absent").  This restates the published soft census / ternary loss of UnFlow (Meister et al., AAAI 2018)
+#   as commonly implemented (7x7 patch, grey*255, t = d/sqrt(0.81+d^2), soft Hamming (dt^2)/(0.1+dt^2), interior mask),
+#   combined with the occlusion weighting of photometric_error (models/model.py:37-46).  There is no reference output
+#   to compare with: the CUDA kernel is checked against THIS function only.
+# --------------------------------------------------------------------------------------------
+
+
+def _grey255(img):
+    if img.shape[1] == 3:
+        g = img[:, 0:1] * 0.2989 + img[:, 1:2] * 0.5870 + img[:, 2:3] * 0.1140
+    else:
+        g = img.mean(dim=1, keepdim=True)
+    return g * 255.0
+
+
+def census_transform(img, max_distance=3):
+    """[B,C,H,W] -> [B,(2m+1)^2,H,W]: soft sign of (neighbour - centre) of the grey image, zero padding."""
+    m = int(max_distance)
+    n = 2 * m + 1
+    g = _grey255(img)
+    B, _, H, W = g.shape
+    gp = F.pad(g, (m, m, m, m))
+    planes = [gp[:, :, iy:iy + H, ix:ix + W] - g for iy in range(n) for ix in range(n)]
+    t = torch.cat(planes, dim=1)
+    return t / torch.sqrt(0.81 + t * t)
+
+
+def census_distance(img1, img2, max_distance=3):
+    """mean over the patch of the soft Hamming distance, zeroed on the m-pixel border -> [B,1,H,W]."""
+    m = int(max_distance)
+    t1, t2 = census_transform(img1, m), census_transform(img2, m)
+    d = (t1 - t2) ** 2
+    dist = (d / (0.1 + d)).mean(dim=1, keepdim=True)
+    valid = torch.zeros_like(dist)
+    H, W = dist.shape[2:]
+    if H > 2 * m and W > 2 * m:
+        valid[:, :, m:H - m, m:W - m] = 1.0
+    return dist * valid, valid
+
+
+def census_loss(img_pred, img, occ=None, max_distance=3):
+    """sum(dist * valid * (1-occ)) / (sum(valid * (1-occ)) + 1e-16); occ [B,1,H,W] as in photometric_error."""
+    dist, valid = census_distance(img_pred, img, max_distance)
+    w = valid if occ is None else valid * (1.0 - occ)
+    return (dist * w).sum() / (w.sum() + 1e-16)
+
+
+# --------------------------------------------------------------------------------------------
 # a-10  FlowNetCV forward, functional over a state_dict    cost_volume_flow_net.py:22-246
 # --------------------------------------------------------------------------------------------
 

@@ -1,0 +1,80 @@
+"""Soft census term (north_star names it; the reference defines none -> PARITY UNPINNED, see oracle census_loss).
+CPU: the oracle restatement is self-consistent (known answers, fp64 gradcheck).  GPU: ocf_census_fwd / ocf_census_bwd
+through the C ABI against the oracle on seeded inputs, odd sizes, all patch radii, with and without occlusion."""
+import pytest
+import torch
+
+from conftest import assert_close, assert_scalar_close
+from oracle import ocflow_oracle as O
+
+
+def _inputs(B, C, H, W, seed, noise=0.05):
+    g = torch.Generator().manual_seed(seed)
+    img = torch.rand(B, C, H, W, generator=g) * 2 - 1
+    pred = img + noise * torch.randn(B, C, H, W, generator=g)
+    occ = (torch.rand(B, 1, H, W, generator=g) < 0.3).float()
+    return pred, img, occ
+
+
+def test_oracle_census_known_answers():
+    pred, img, occ = _inputs(2, 3, 12, 14, 0)
+    assert float(O.census_loss(img, img, occ)) == 0.0
+    # a constant offset leaves every (neighbour - centre) difference unchanged
+    assert float(O.census_loss(img + 0.25, img)) < 1e-6
+    # saturation: opposite soft signs everywhere -> dt^2/(0.1+dt^2) -> close to 4/4.1 (the centre tap contributes 0)
+    big = torch.randn(1, 3, 9, 9) * 10
+    v = float(O.census_loss(-big, big, None, 1))
+    assert 0.5 < v < 8.0 / 9.0 * (4 / 4.1) + 1e-6
+    # the border of width m carries no weight
+    d, valid = O.census_distance(pred, img, 3)
+    assert float(valid[:, :, :3].sum()) == 0 and float(valid[:, :, :, -3:].sum()) == 0
+    assert float(valid.sum()) == 2 * (12 - 6) * (14 - 6)
+    # images smaller than the border: no valid pixel, loss 0 (not NaN)
+    assert float(O.census_loss(torch.rand(1, 3, 5, 5), torch.rand(1, 3, 5, 5), None, 3)) == 0.0
+
+
+def test_oracle_census_gradcheck_fp64():
+    pred, img, occ = _inputs(1, 3, 9, 10, 1, noise=0.002)
+    pred = pred.double().requires_grad_(True)
+    assert torch.autograd.gradcheck(lambda p: O.census_loss(p, img.double(), occ.double(), 2), (pred,), eps=1e-7, atol=1e-7, rtol=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,m,use_occ", [((2, 3, 37, 45), 3, True), ((1, 3, 16, 32), 3, False), ((2, 3, 33, 70), 2, True),
+                                              ((1, 1, 20, 21), 1, True), ((1, 3, 6, 40), 3, True), ((3, 2, 17, 19), 2, False)])
+def test_cuda_census_matches_oracle(shape, m, use_occ):
+    import ocflow_b200 as ocf
+
+    for noise in (0.05, 0.002):   # far from / close to the steep part of the soft sign
+        pred, img, occ = _inputs(*shape, seed=7, noise=noise)
+        occ = occ if use_occ else None
+        p_ref = pred.clone().requires_grad_(True)
+        ref = O.census_loss(p_ref, img, occ, m)
+        ref.backward()
+        p = pred.cuda().requires_grad_(True)
+        mine = ocf.census_loss(p, img.cuda(), None if occ is None else occ.cuda(), m)
+        assert_scalar_close(mine, ref, 1e-3 if float(ref) > 0 else 1e-9, "census loss")
+        mine.backward()
+        if float(p_ref.grad.abs().max()) > 0:
+            assert_close(p.grad, p_ref.grad, 1e-4, "d census / d pred")
+        else:
+            assert float(p.grad.abs().max()) == 0.0
+
+
+@pytest.mark.gpu
+def test_cuda_census_full_size_properties():
+    """Sintel shape (config 4): identical images -> exactly 0; constant offset -> ~0; occluding everything -> 0 weight."""
+    import ocflow_b200 as ocf
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    img = torch.rand(2, 3, 436, 1024, device="cuda", generator=g) * 2 - 1
+    assert float(ocf.census_loss(img, img)) == 0.0
+    assert float(ocf.census_loss(img + 0.5, img)) < 1e-5
+    occ = torch.ones(2, 1, 436, 1024, device="cuda")
+    assert float(ocf.census_loss(img * 0.5, img, occ)) == 0.0
+    noisy = (img + 0.1 * torch.randn(img.shape, device="cuda", generator=g)).requires_grad_(True)
+    l = ocf.census_loss(noisy, img)
+    l.backward()
+    assert 0 < float(l) < 1 and torch.isfinite(noisy.grad).all()
+    # the term is invariant to a global intensity offset of the prediction -> the gradient sums to ~0 per channel
+    assert abs(float(noisy.grad.sum())) < 1e-3 * float(noisy.grad.abs().sum())
