@@ -36,7 +36,8 @@ __device__ __forceinline__ float grey255(const float* __restrict__ img, int C, i
   return g * 255.0f;
 }
 
-__device__ __forceinline__ float soft_sign(float u) { return u * rsqrtf(fmaf(u, u, 0.81f)); }
+// the product is rounded on its own (no FMA contraction with the subtraction that follows), so identical inputs give exactly 0
+__device__ __forceinline__ float soft_sign(float u) { return __fmul_rn(u, rsqrtf(fmaf(u, u, 0.81f))); }
 
 template <int M, int HALO>
 __device__ __forceinline__ void stage_grey(float (*g1)[CT_W + 2 * HALO], float (*g2)[CT_W + 2 * HALO], const float* __restrict__ a,
@@ -109,7 +110,7 @@ census_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ img,
   auto G = [&](int py, int px, int ny, int nx) -> float {
     const float up = gp[ny][nx] - gp[py][px], ui = gi[ny][nx] - gi[py][px];
     const float rp = rsqrtf(fmaf(up, up, 0.81f));
-    const float diff = up * rp - ui * rsqrtf(fmaf(ui, ui, 0.81f));
+    const float diff = __fmul_rn(up, rp) - __fmul_rn(ui, rsqrtf(fmaf(ui, ui, 0.81f)));
     const float d = diff * diff;
     const float den = __fdividef(1.0f, 0.1f + d);
     // d/dt (t-ti)^2/(0.1+(t-ti)^2) = 0.2 diff / (0.1+d)^2 ;  dt/du = 0.81 (0.81+u^2)^-1.5
