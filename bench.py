@@ -341,6 +341,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout carries exactly ONE JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION|INFO) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from ocflow_b200 import _lib
     from ocflow_b200.train import TrainStep, build_model, synthetic_batch
