@@ -673,15 +673,12 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
       if (lane == 0) {
         // coefficient boxes: mode 0 -> planes dy*ND.. at (y0, x0) ; mode 1 -> planes (2D-dy)*ND.. at (y0+dy-D, x0-D)
         constexpr unsigned GBYTES = sizeof(float) * ND * BOXG;
-        for (int pass = 0; pass < (has_act ? 2 : 1); ++pass) {
-          if (pass == 1) mbar_wait(&gdone_bar, 0);  // every warp has lifted its coefficients out of the staging area
-          mbar_expect_tx(&g_bar, GBYTES);
-          for (int w = 0; w < ND; ++w) {
-            const int plane0 = mode == 0 ? w * ND : (2 * D - w) * ND;
-            tma_load_4d(smem + w * BOXG, pass == 0 ? &mapg : &mapa, &g_bar, mode == 0 ? x0 : x0 - D, mode == 0 ? y0 : y0 + w - D, plane0, b);
-          }
+        mbar_expect_tx(&g_bar, GBYTES);
+        for (int w = 0; w < ND; ++w) {
+          const int plane0 = mode == 0 ? w * ND : (2 * D - w) * ND;
+          tma_load_4d(smem + w * BOXG, &mapg, &g_bar, mode == 0 ? x0 : x0 - D, mode == 0 ? y0 : y0 + w - D, plane0, b);
         }
-        mbar_wait(&gdone_bar, has_act ? 1 : 0);  // staging area is free: start feeding the feature ring
+        mbar_wait(&gdone_bar, 0);  // every warp has lifted its coefficients out of the staging area: feed the feature ring
         constexpr unsigned BYTES = sizeof(float) * T::F2_STAGE;
         const CUtensorMap* map = mode == 0 ? &map2 : &map1;  // the OTHER feature
         for (int i = 0; i < nchunks; ++i) {
@@ -693,43 +690,76 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
       }
       return;  // the producer warp takes no part in the compute-warp barriers below
     }
-    const float* gw = smem + dyi * BOXG + ty * GW + tx * PX;
-    for (int pass = 0; pass < (has_act ? 2 : 1); ++pass) {
-      mbar_wait(&g_bar, pass);
+    // LeakyReLU mask: the sign of the activated forward output at this thread's 81 coefficient positions, fetched straight
+    // from global memory into a 72-bit register mask WHILE the coefficient boxes are in flight (a second TMA pass over the
+    // staging area would serialise another L2 round trip + lift behind the first).  Where the coefficient itself is a
+    // zero-filled out-of-image element the mask value is irrelevant, so addresses are clamped instead of predicated
+    // (W % 4 == 0 on this path: an aligned group of 4 is entirely inside or entirely outside the row).
+    unsigned mbits[3] = {0u, 0u, 0u};  // bit (dx % 3) * PX + p of word dx / 3
+    if (has_act) {
+      static_assert(ND == 9 && PX == 8, "mask packing assumes 9 displacements x 8 pixels");
+      const float* ap = oact + ab;
+      const int xs = x0 + tx * PX;
       if (mode == 0) {
+        const int y = min(y0 + ty, H - 1);
 #pragma unroll
         for (int dx = 0; dx < ND; ++dx) {
-          float t[PX];
+          const float* row = ap + ((size_t)(dyi * ND + dx) * H + y) * W;
 #pragma unroll
           for (int q = 0; q < PX / 4; ++q) {
-            const float4 v = *reinterpret_cast<const float4*>(gw + dx * TH * GW + 4 * q);
-            t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
-          }
-#pragma unroll
-          for (int p = 0; p < PX; ++p) {
-            if (pass == 0) G[dx][p] = t[p];
-            else if (!(t[p] > 0.f)) G[dx][p] *= slope;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(row + min(xs + 4 * q, W - 4)));
+            const unsigned m = (v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u);
+            mbits[dx / 3] |= m << ((dx % 3) * PX + 4 * q);
           }
         }
       } else {
+        const int sy = min(max(y0 + ty + dyi - D, 0), H - 1);
 #pragma unroll
         for (int dx = 0; dx < ND; ++dx) {
-          float t[PX + 4];
+          const float* row = ap + ((size_t)((2 * D - dyi) * ND + (2 * D - dx)) * H + sy) * W;
+          const int cb = xs - D + (dx & ~3);  // aligned group holding the first needed column xs + dx - D
+          unsigned m = 0u;                    // 12 sign bits of columns cb .. cb + 11
 #pragma unroll
           for (int q = 0; q < PX / 4 + 1; ++q) {
-            const float4 v = *reinterpret_cast<const float4*>(gw + (2 * D - dx) * TH * GW + (dx & ~3) + 4 * q);
-            t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(row + min(max(cb + 4 * q, 0), W - 4)));
+            m |= ((v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u)) << (4 * q);
           }
-#pragma unroll
-          for (int p = 0; p < PX; ++p) {
-            const float v = t[p + (dx & 3)];
-            if (pass == 0) G[dx][p] = v;
-            else if (!(v > 0.f)) G[dx][p] *= slope;
-          }
+          mbits[dx / 3] |= ((m >> (dx & 3)) & 0xffu) << ((dx % 3) * PX);
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&gdone_bar);
+    }
+    const float* gw = smem + dyi * BOXG + ty * GW + tx * PX;
+    mbar_wait(&g_bar, 0);
+    if (mode == 0) {
+#pragma unroll
+      for (int dx = 0; dx < ND; ++dx) {
+#pragma unroll
+        for (int q = 0; q < PX / 4; ++q) {
+          const float4 v = *reinterpret_cast<const float4*>(gw + dx * TH * GW + 4 * q);
+          G[dx][4 * q] = v.x; G[dx][4 * q + 1] = v.y; G[dx][4 * q + 2] = v.z; G[dx][4 * q + 3] = v.w;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int dx = 0; dx < ND; ++dx) {
+        float t[PX + 4];
+#pragma unroll
+        for (int q = 0; q < PX / 4 + 1; ++q) {
+          const float4 v = *reinterpret_cast<const float4*>(gw + (2 * D - dx) * TH * GW + (dx & ~3) + 4 * q);
+          t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int p = 0; p < PX; ++p) G[dx][p] = t[p + (dx & 3)];
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&gdone_bar);
+    if (has_act) {
+#pragma unroll
+      for (int dx = 0; dx < ND; ++dx)
+#pragma unroll
+        for (int p = 0; p < PX; ++p)
+          if (!((mbits[dx / 3] >> ((dx % 3) * PX + p)) & 1u)) G[dx][p] *= slope;
     }
   }
   const float* fo = (mode == 0 ? f2 : f1) + (size_t)b * C * H * W;
