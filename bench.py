@@ -46,9 +46,11 @@ def parse():
     ap.add_argument("--width", type=int, default=512)
     ap.add_argument("--graph", type=int, default=1, help="capture the whole step in a CUDA graph (1) or run eagerly (0)")
     ap.add_argument("--tf32", type=int, default=0, help="allow TF32 cuDNN convolutions (torch's default); 0 = strict fp32")
+    ap.add_argument("--channels-last", type=int, default=0, help="experiment: keep the conv stacks in NHWC (cuDNN channels_last kernels)")
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-roofline", action="store_true")
+    ap.add_argument("--skip-alt", action="store_true", help="skip the informational TF32-convolution leg (N=1 only)")
     ap.add_argument("--kernels-only", action="store_true", help="only time the hot-path kernels alone (developer aid)")
     ap.add_argument("--cuda-profiler-range", action="store_true",
                     help="bracket the timed region with cudaProfilerStart/Stop (use with ncu --profile-from-start off)")
@@ -363,6 +365,8 @@ def main():
     torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
     B, H, W = args.batch, args.height, args.width
     model = build_model(seed=0)
+    if args.channels_last:
+        model = model.to(memory_format=torch.channels_last)
     step = TrainStep(model, use_graph=bool(args.graph))
     batch = synthetic_batch(B, H, W, "cuda", 1234 + rank)
 
@@ -488,6 +492,34 @@ def main():
                            for k, v in kt.items()}
         line["hot_path_us_per_step"] = round(sum(v["us"] * v["per_step"] for v in kt.values()), 1)
         line["hot_path_live_us_per_step"] = round(sum(t * n for t, n in live.values()), 1)
+
+    # ---- informational: the same step under torch's DEFAULT conv math (TF32 tensor cores for cuDNN convolutions) ----
+    # Not the headline: `value` above is strict fp32 so that "matches the fp32 reference" holds for the whole step.  The
+    # hot-path kernels are fp32 in both; only the cuDNN conv stacks change.  Reported with the step-0 loss difference so the
+    # precision cost of the policy is visible next to its speed.
+    if world == 1 and not args.skip_alt and not args.tf32:
+        with torch.no_grad():
+            ref_model = build_model(seed=0)
+            l32 = float(ref_model.training_step(batch, 0))
+            torch.backends.cudnn.allow_tf32 = True
+            ltf = float(ref_model.training_step(batch, 0))
+        del ref_model
+        alt_step = TrainStep(build_model(seed=0), use_graph=bool(args.graph))
+        for _ in range(3):
+            alt_step.step(batch)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(args.steps):
+            alt_step.step(batch)
+        a1.record()
+        torch.cuda.synchronize()
+        adt = a0.elapsed_time(a1) * 1e-3
+        torch.backends.cudnn.allow_tf32 = False
+        line["alt_tf32_convs"] = {"value": B * args.steps / adt, "unit": UNIT, "ms_per_step": 1e3 * adt / args.steps,
+                                  "conv_math": "tf32 (torch's default cudnn.allow_tf32=True); hot-path kernels unchanged (fp32)",
+                                  "step0_loss_fp32": l32, "step0_loss_tf32": ltf, "step0_loss_rel_diff": abs(ltf - l32) / abs(l32)}
+        del alt_step
 
     # ---- CPU baseline (oracle port), bounded sample ----
     if world == 1 and not args.skip_cpu:
