@@ -266,3 +266,37 @@ def test_ssim_matches_oracle_value_and_gradients(shape, ws):
         assert_close(bc.grad, b.grad, 2e-4, "d ssim / d img2")
     loss = ocf.ssim_photometric_loss(i1.cuda(), i2.cuda(), ws)
     assert_scalar_close(loss, (1 - O.ssim(i1, i2, ws)) / 2, LOSS_TOL)
+
+
+@pytest.mark.parametrize("B,C,H,W", [(4, 20, 56, 96), (3, 8, 61, 100), (2, 41, 75, 128), (5, 32, 48, 72)])
+@pytest.mark.parametrize("slope", [1.0, 0.1])
+def test_corr_persistent_kernels_match_oracle(B, C, H, W, slope):
+    """Shapes with at least one tile (forward) / one (tile, gradient) item (backward) per SM take the persistent kernels:
+    several items per CTA, coefficient planes of the next item prefetched during the current main loop, mask bits of the
+    next item fetched between channel chunks.  Channel tails (C % 8 != 0), row / column overhang and gradients that arrive
+    as concat slices are covered; each gradient is also requested alone (one item per tile instead of two)."""
+    from ocflow_b200 import ops
+
+    g = torch.Generator().manual_seed(B * 7919 + C * 31 + H + W)
+    f1, f2 = torch.randn(B, C, H, W, generator=g), torch.randn(B, C, H, W, generator=g) + 0.2
+    other = torch.randn(B, 3, H, W, generator=g)
+    cot = torch.randn(B, 3 + 81, H, W, generator=g)
+    orc = (lambda a, b: torch.nn.functional.leaky_relu(O.cost_volume(a, b, 4), slope)) if slope != 1.0 else (lambda a, b: O.cost_volume(a, b, 4))
+
+    def run(corr, dev, need=(True, True), dtype=torch.float32):
+        a = f1.clone().to(dev, dtype).requires_grad_(need[0])
+        b = f2.clone().to(dev, dtype).requires_grad_(need[1])
+        out = corr(a, b)
+        cat = torch.cat((other.to(dev, dtype), out), 1)        # the gradient of `out` arrives as a channel slice
+        (cat * cot.to(dev, dtype)).sum().backward()
+        return out.detach(), a.grad, b.grad
+
+    want = run(orc, "cpu", dtype=torch.float64)
+    mine = run(lambda a, b: ops.cost_volume(a, b, 4, leaky_slope=slope), "cuda")
+    for m, w, name in zip(mine, want, ("corr", "d f1", "d f2")):
+        assert_close(m, w, TOL, name)
+    only1 = run(lambda a, b: ops.cost_volume(a, b, 4, leaky_slope=slope), "cuda", need=(True, False))
+    only2 = run(lambda a, b: ops.cost_volume(a, b, 4, leaky_slope=slope), "cuda", need=(False, True))
+    assert only1[2] is None and only2[1] is None
+    assert_close(only1[1], want[1], TOL, "d f1 alone")
+    assert_close(only2[2], want[2], TOL, "d f2 alone")
