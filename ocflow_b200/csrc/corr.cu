@@ -863,274 +863,6 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
   if constexpr (!TMA) cp_async_wait<0>();
 }
 
-// ---- backward, persistent (regular shapes, no channel split) ---------------------------------------
-// One CTA per SM walks the (tile, mode) items blockIdx.x, blockIdx.x + gridDim.x, ...  Shared memory holds the
-// coefficient staging area, the feature ring and the reduction buffer SIDE BY SIDE (218 KB), so the producer thread can
-// put the NEXT item's 81 coefficient planes in flight as soon as every warp has lifted the current ones, and the feature
-// ring never drains between items: the per-tile prologue (one L2/DRAM round trip + lift, as expensive as ~30 channels
-// of main loop in the one-tile-per-CTA kernel) is paid once per CTA instead of once per tile.  The LeakyReLU mask of
-// the next item is fetched in three batches of three displacements interleaved with the main loop of the current one
-// (issued at the top of a channel chunk, turned into register bits at the top of the next).
-template <int PX>
-struct MaskBatch {
-  float4 v[3][PX / 4 + 1];
-};
-
-template <class T>
-__device__ __forceinline__ void mask_issue(MaskBatch<T::PX>& mb, const float* __restrict__ ap, int batch, int mode, int dyi, int ty,
-                                           int tx, int x0, int y0, int H, int W) {
-  constexpr int D = T::D, PX = T::PX, ND = T::ND;
-  const int xs = x0 + tx * PX;
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    const int dx = 3 * batch + j;
-    if (mode == 0) {
-      const float* row = ap + ((size_t)(dyi * ND + dx) * H + min(y0 + ty, H - 1)) * W;
-#pragma unroll
-      for (int q = 0; q < PX / 4; ++q) mb.v[j][q] = __ldg(reinterpret_cast<const float4*>(row + min(xs + 4 * q, W - 4)));
-    } else {
-      const float* row = ap + ((size_t)((2 * D - dyi) * ND + (2 * D - dx)) * H + min(max(y0 + ty + dyi - D, 0), H - 1)) * W;
-      const int cb = xs - D + (dx & ~3);
-#pragma unroll
-      for (int q = 0; q < PX / 4 + 1; ++q) mb.v[j][q] = __ldg(reinterpret_cast<const float4*>(row + min(max(cb + 4 * q, 0), W - 4)));
-    }
-  }
-}
-
-// sign bits of one batch: bit j * PX + p  <->  displacement 3 * batch + j, pixel p
-template <class T>
-__device__ __forceinline__ unsigned mask_bits(const MaskBatch<T::PX>& mb, int batch, int mode) {
-  constexpr int PX = T::PX;
-  unsigned word = 0u;
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    const int dx = 3 * batch + j;
-    unsigned m = 0u;
-#pragma unroll
-    for (int q = 0; q < PX / 4 + 1; ++q) {
-      if (q == PX / 4 && mode == 0) break;  // the third group is only loaded (and needed) for the shifted planes of mode 1
-      const float4 v = mb.v[j][q];
-      m |= ((v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u)) << (4 * q);
-    }
-    const int shift = mode == 0 ? 0 : (dx & 3);
-    word |= ((m >> shift) & ((1u << PX) - 1u)) << (j * PX);
-  }
-  return word;
-}
-
-// runtime-indexed store into a 3-word register array without demoting it to local memory
-__device__ __forceinline__ void set_word(unsigned (&w)[3], int i, unsigned v) {
-  if (i == 0) w[0] = v;
-  else if (i == 1) w[1] = v;
-  else w[2] = v;
-}
-
-template <class T, int CR>
-__global__ void __launch_bounds__(T::THREADS + 32, 1)
-corr_bwd_persist(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
-                 const __grid_constant__ CUtensorMap mapg, const float* __restrict__ oact, float* __restrict__ df1,
-                 float* __restrict__ df2, int C, int H, int W, long long a_bstride, float inv_c, float slope, int nmodes,
-                 int first_mode, int tiles_x, int tiles_y, int nitems) {
-  constexpr int D = T::D, PX = T::PX, ND = T::ND, TH = T::TH, TW = T::TW, CC = T::CC, STAGES = T::STAGES;
-  constexpr int S1 = T::S1, S2 = T::S2, F2H = T::F2H, WIN = T::WIN;
-  constexpr int GW = T::S2, BOXG = ND * TH * GW;
-  static_assert(CC % CR == 0, "CC must be a multiple of CR");
-  static_assert(ND == 9 && PX == 8, "mask packing assumes 9 displacements x 8 pixels");
-  extern __shared__ __align__(128) float smem[];
-  __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES], g_bar, gdone_bar;
-  float* stg = smem;                             // [ND][ND][TH][GW] coefficient planes of the item being lifted / prefetched
-  float* ring = smem + ND * BOXG;                // [STAGES][CC][F2H][S2]
-  float* red = ring + STAGES * T::F2_STAGE;      // [ND][CR][TH][S1]
-
-  const int tid = threadIdx.x;
-  const int lane = tid % T::LANES;
-  const int tx = lane % T::TXT, ty = lane / T::TXT;
-  const int dyi = tid / T::LANES;  // == ND for the TMA producer warp
-  const int nchunks = (C + CC - 1) / CC;
-  const int nit = ((int)blockIdx.x < nitems) ? (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const bool has_act = oact != nullptr;
-  const size_t abs_ = a_bstride ? (size_t)a_bstride : (size_t)ND * ND * H * W;
-
-  struct Item {
-    int x0, y0, b, mode;
-  };
-  auto decode = [&](int k) -> Item {
-    const int item = (int)blockIdx.x + k * (int)gridDim.x;
-    const int tile = item / nmodes;
-    const int txi = tile % tiles_x, r = tile / tiles_x;
-    Item it;
-    it.mode = first_mode + (item - tile * nmodes);
-    it.x0 = txi * TW;
-    it.y0 = (r % tiles_y) * TH;
-    it.b = r / tiles_y;
-    return it;
-  };
-
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ND); }
-    mbar_init(&g_bar, 1);
-    mbar_init(&gdone_bar, ND);
-    mbar_fence_init();
-  }
-  __syncthreads();
-
-  if (dyi == ND) {
-    if (lane == 0 && nit > 0) {
-      constexpr unsigned GBYTES = sizeof(float) * ND * BOXG;
-      constexpr unsigned BYTES = sizeof(float) * T::F2_STAGE;
-      // coefficient boxes: mode 0 -> planes dy*ND.. at (y0, x0) ; mode 1 -> planes (2D-dy)*ND.. at (y0+dy-D, x0-D)
-      auto issue_g = [&](const Item& it) {
-        mbar_expect_tx(&g_bar, GBYTES);
-        for (int w = 0; w < ND; ++w) {
-          const int plane0 = it.mode == 0 ? w * ND : (2 * D - w) * ND;
-          tma_load_4d(stg + w * BOXG, &mapg, &g_bar, it.mode == 0 ? it.x0 : it.x0 - D, it.mode == 0 ? it.y0 : it.y0 + w - D, plane0, it.b);
-        }
-      };
-      issue_g(decode(0));
-      int n = 0;  // flat chunk counter of this CTA
-      const int head = nchunks < STAGES ? nchunks : STAGES;
-      for (int k = 0; k < nit; ++k) {
-        const Item it = decode(k);
-        const CUtensorMap* map = it.mode == 0 ? &map2 : &map1;  // the OTHER feature
-        for (int i = 0; i < nchunks; ++i, ++n) {
-          if (i == head) {  // the ring is primed for this item: now swap the staging area over to the next item
-            mbar_wait(&gdone_bar, k & 1);
-            if (k + 1 < nit) issue_g(decode(k + 1));
-          }
-          const int s = n % STAGES;
-          if (n >= STAGES) mbar_wait(&empty_bar[s], ((n / STAGES) - 1) & 1);
-          mbar_expect_tx(&full_bar[s], BYTES);
-          tma_load_4d(ring + s * T::F2_STAGE, map, &full_bar[s], it.x0 - D, it.y0 - D, i * CC, it.b);
-        }
-        if (nchunks <= head) {
-          mbar_wait(&gdone_bar, k & 1);
-          if (k + 1 < nit) issue_g(decode(k + 1));
-        }
-      }
-    }
-    return;  // the producer warp takes no part in the compute-warp barriers below
-  }
-
-  float G[ND][PX];       // 81 per-pixel coefficients of this thread's dy row
-  unsigned nbits[3] = {0u, 0u, 0u};  // mask of the item about to be lifted (bit (dx % 3) * PX + p of word dx / 3)
-  MaskBatch<PX> mb;
-  if (has_act && nit > 0) {  // first item: nothing to overlap with
-    const Item it = decode(0);
-#pragma unroll
-    for (int bt = 0; bt < 3; ++bt) {
-      mask_issue<T>(mb, oact + abs_ * it.b, bt, it.mode, dyi, ty, tx, it.x0, it.y0, H, W);
-      nbits[bt] = mask_bits<T>(mb, bt, it.mode);
-    }
-  }
-  int n = 0;
-  for (int k = 0; k < nit; ++k) {
-    const Item it = decode(k);
-    const float* gw = stg + dyi * BOXG + ty * GW + tx * PX;
-    mbar_wait(&g_bar, k & 1);
-    if (it.mode == 0) {
-#pragma unroll
-      for (int dx = 0; dx < ND; ++dx) {
-#pragma unroll
-        for (int q = 0; q < PX / 4; ++q) {
-          const float4 v = *reinterpret_cast<const float4*>(gw + dx * TH * GW + 4 * q);
-          G[dx][4 * q] = v.x; G[dx][4 * q + 1] = v.y; G[dx][4 * q + 2] = v.z; G[dx][4 * q + 3] = v.w;
-        }
-      }
-    } else {
-#pragma unroll
-      for (int dx = 0; dx < ND; ++dx) {
-        float t[PX + 4];
-#pragma unroll
-        for (int q = 0; q < PX / 4 + 1; ++q) {
-          const float4 v = *reinterpret_cast<const float4*>(gw + (2 * D - dx) * TH * GW + (dx & ~3) + 4 * q);
-          t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
-        }
-#pragma unroll
-        for (int p = 0; p < PX; ++p) G[dx][p] = t[p + (dx & 3)];
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&gdone_bar);
-    if (has_act) {
-#pragma unroll
-      for (int dx = 0; dx < ND; ++dx)
-#pragma unroll
-        for (int p = 0; p < PX; ++p)
-          if (!((nbits[dx / 3] >> ((dx % 3) * PX + p)) & 1u)) G[dx][p] *= slope;
-    }
-    // mask prefetch state for item k + 1
-    const bool more = has_act && k + 1 < nit;
-    Item nx = it;
-    if (more) nx = decode(k + 1);
-    const float* nap = more ? oact + abs_ * nx.b : nullptr;
-    int issued = 0, done = 0;  // batches issued / converted
-
-    float* dout = (it.mode == 0 ? df1 : df2) + (size_t)it.b * C * H * W;
-    for (int i = 0; i < nchunks; ++i, ++n) {
-      if (more) {
-        if (done < issued) { set_word(nbits, done, mask_bits<T>(mb, done, nx.mode)); ++done; }
-        if (issued < 3) { mask_issue<T>(mb, nap, issued, nx.mode, dyi, ty, tx, nx.x0, nx.y0, H, W); ++issued; }
-      }
-      const int s = n % STAGES;
-      mbar_wait(&full_bar[s], (n / STAGES) & 1);
-      const int c0 = i * CC;
-      const float* pw = ring + s * T::F2_STAGE + (ty + dyi) * S2 + tx * PX;
-#pragma unroll 1
-      for (int r0 = 0; r0 < CC; r0 += CR) {
-        if (c0 + r0 >= C) break;  // uniform across the block
-#pragma unroll
-        for (int c = 0; c < CR; ++c) {
-          float w[WIN], part[PX];
-#pragma unroll
-          for (int q = 0; q < WIN / 4; ++q) {
-            const float4 v = *reinterpret_cast<const float4*>(pw + (r0 + c) * F2H * S2 + 4 * q);
-            w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
-          }
-#pragma unroll
-          for (int p = 0; p < PX; ++p) part[p] = 0.f;
-#pragma unroll
-          for (int dx = 0; dx < ND; ++dx)
-#pragma unroll
-            for (int p = 0; p < PX; ++p) part[p] = fmaf(G[dx][p], w[p + dx], part[p]);
-          float* rp = red + ((dyi * CR + c) * TH + ty) * S1 + tx * PX;
-#pragma unroll
-          for (int q = 0; q < PX / 4; ++q)
-            *reinterpret_cast<float4*>(rp + 4 * q) = make_float4(part[4 * q], part[4 * q + 1], part[4 * q + 2], part[4 * q + 3]);
-        }
-        consumer_bar_sync<T::THREADS>();
-        // cross-dy reduction: CR*TH*TW/4 float4 outputs
-        constexpr int OUT4 = CR * TH * TW / 4;
-        for (int j = tid; j < OUT4; j += T::THREADS) {
-          const int x4 = j % (TW / 4), row = j / (TW / 4);  // row = c*TH + ry
-          const int c = row / TH, ry = row - c * TH;
-          float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int q = 0; q < ND; ++q) {
-            const float4 v = *reinterpret_cast<const float4*>(red + ((q * CR + c) * TH + ry) * S1 + x4 * 4);
-            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
-          }
-          const int ch = c0 + r0 + c, y = it.y0 + ry, x = it.x0 + x4 * 4;
-          if (ch < C && y < H && x < W)
-            *reinterpret_cast<float4*>(dout + ((size_t)ch * H + y) * W + x) =
-                make_float4(sum.x * inv_c, sum.y * inv_c, sum.z * inv_c, sum.w * inv_c);
-        }
-        consumer_bar_sync<T::THREADS>();
-      }
-      // the last consumer barrier above ordered every warp's reads of this stage: one arrival per warp frees it
-      if (lane == 0) mbar_arrive(&empty_bar[s]);
-    }
-    if (more) {  // batches that did not fit between the chunks of a short item
-      if (done < issued) { set_word(nbits, done, mask_bits<T>(mb, done, nx.mode)); ++done; }
-      while (issued < 3) {
-        mask_issue<T>(mb, nap, issued, nx.mode, dyi, ty, tx, nx.x0, nx.y0, H, W);
-        set_word(nbits, issued, mask_bits<T>(mb, issued, nx.mode));
-        ++issued;
-      }
-    }
-  }
-}
-
 // generic-displacement backward: one thread per (b, c, y, x) element of d f1 / d f2.
 __global__ void __launch_bounds__(128)
 corr_bwd_generic(const float* __restrict__ g, const float* __restrict__ oact, const float* __restrict__ f1,
@@ -1344,15 +1076,7 @@ extern "C" int ocf_corr_bwd(const float* grad_out, const float* out_act, const f
     tma = tma && make_map(&m1, f1, B, C, H, W, T::S2, T::F2H, T::CC) && make_map(&m2, f2, B, C, H, W, T::S2, T::F2H, T::CC) &&
           make_map(&mg, grad_out, B, (int)(nd * nd), H, W, T::S2, T::TH, T::ND, gbs) &&
           (out_act == nullptr || make_map(&ma, out_act, B, (int)(nd * nd), H, W, T::S2, T::TH, T::ND, abs_));
-    const long long items = (long long)gx * gy * B * nmodes;
-    if (tma && ks == 1 && items >= OCF_SM_COUNT && getenv("OCF_BWD_NO_PERSIST") == nullptr) {
-      const size_t gstage = sizeof(float) * T::ND * T::ND * T::TH * T::S2;
-      const size_t psmem = gstage + smem;  // staging + ring + reduction buffer side by side
-      auto kernel = corr_bwd_persist<T, BWD_CR>;
-      if (int e = set_smem(kernel, psmem)) return e;
-      if (int e = launch_kernel(kernel, dim3(OCF_SM_COUNT), T::THREADS + 32, psmem, s, 1, m1, m2, mg, out_act, df1, df2, C, H, W,
-                                act_bstride, inv_c, leaky_slope, nmodes, first, gx, gy, (int)items)) return e;
-    } else if (tma) {
+    if (tma) {
       const size_t gstage = sizeof(float) * T::ND * T::ND * T::TH * T::S2;  // coefficient staging, reused by ring + red
       if (gstage > smem) smem = gstage;
       auto kernel = corr_bwd_tiled<T, BWD_CR, STG_TMA>;

@@ -271,10 +271,10 @@ def test_ssim_matches_oracle_value_and_gradients(shape, ws):
 @pytest.mark.parametrize("B,C,H,W", [(4, 20, 56, 96), (3, 8, 61, 100), (2, 41, 75, 128), (5, 32, 48, 72)])
 @pytest.mark.parametrize("slope", [1.0, 0.1])
 def test_corr_persistent_kernels_match_oracle(B, C, H, W, slope):
-    """Shapes with at least one tile (forward) / one (tile, gradient) item (backward) per SM take the persistent kernels:
-    several items per CTA, coefficient planes of the next item prefetched during the current main loop, mask bits of the
-    next item fetched between channel chunks.  Channel tails (C % 8 != 0), row / column overhang and gradients that arrive
-    as concat slices are covered; each gradient is also requested alone (one item per tile instead of two)."""
+    """Shapes with at least one tile per SM: the forward takes the persistent kernel (several tiles per CTA, TMA ring running
+    across tile boundaries) and the backward runs its one-tile CTAs in several rounds with the LeakyReLU mask fetched into
+    register bits.  Channel tails (C % 8 != 0), row / column overhang and gradients that arrive as concat slices are
+    covered; each gradient is also requested alone (one CTA per tile instead of two)."""
     from ocflow_b200 import ops
 
     g = torch.Generator().manual_seed(B * 7919 + C * 31 + H + W)
