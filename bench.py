@@ -35,6 +35,12 @@ METRIC = "image pairs/sec (fwd+bwd flow+occ step, 384x512)"
 UNIT = "pairs/s"
 
 
+def workload(height, width, batch):
+    """BASELINE.json configs[1] (configs[2] under torchrun); the same string on both arms."""
+    return ("unsupervised flow+occlusion training step (FlowNetCV 'pwc', occ_aware), FlyingChairs shape %dx%d, "
+            "batch %d per GPU, Adam" % (height, width, batch))
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -162,8 +168,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "unsupervised flow+occlusion training step, FlyingChairs shape %dx%d, batch %d per GPU" % (
-            args.height, args.width, args.batch), "cpu_sample_batch": b},
+        "config": {"workload": workload(args.height, args.width, args.batch), "cpu_sample_batch": b},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -343,9 +348,24 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        # stdout carries exactly ONE JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION|INFO) goes to stderr
+        # stdout carries exactly ONE JSON line.  NCCL prints its version banner with printf-to-stdout semantics when
+        # NCCL_DEBUG=VERSION (NCCL_DEBUG_FILE is only honoured above that level), so the communicator is brought up --
+        # init + one tiny all-reduce -- with file descriptor 1 pointing at stderr, then stdout is restored.
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION",):
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            probe = torch.ones(1, device="cuda")
+            dist.all_reduce(probe)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     from ocflow_b200 import _lib
     from ocflow_b200.train import TrainStep, build_model, synthetic_batch
 
@@ -456,8 +476,7 @@ def main():
         "metric": METRIC, "value": world * B * args.steps / dt, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "unsupervised flow+occlusion training step (FlowNetCV 'pwc', occ_aware), FlyingChairs shape %dx%d, "
-                               "batch %d per GPU, Adam" % (H, W, B),
+        "config": {"workload": workload(H, W, B),
                    "global_batch": world * B, "parallelism": "dp%d" % world, "cuda_graph": bool(args.graph),
                    "conv_math": "tf32 (torch default)" if args.tf32 else "strict fp32 (cudnn.allow_tf32=False)",
                    "l2_policy": "working set per step (>1 GB of activations) exceeds the 126 MB L2; kernel-alone timings flush L2 "
