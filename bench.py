@@ -210,13 +210,14 @@ def kernel_table(args, torch):
         fl = smooth_flow(B, h, w, 2.0)
         out = torch.empty(B, 81, h, w, device=dev)
         gout = torch.randn(B, 81, h, w, device=dev, generator=g)
+        msk = torch.zeros(B, 81, h, (w + 7) // 8, device=dev, dtype=torch.uint8)   # LeakyReLU sign bitmask (fwd writes, bwd reads)
         d1, d2 = torch.empty_like(f1), torch.empty_like(f2)
         wout = torch.empty_like(f2)
         dfl = torch.empty_like(fl)
-        table["corr_fwd_L%d" % lvl] = (lambda f1=f1, f2=f2, out=out, C=C, h=h, w=w: _lib.call(
-            "ocf_corr_fwd", P(f1), P(f2), P(out), B, C, h, w, 4, 0, 0.1, None, st), 4 * n * (2 * C + 81), 2)
-        table["corr_bwd_L%d" % lvl] = (lambda gout=gout, out=out, f1=f1, f2=f2, d1=d1, d2=d2, C=C, h=h, w=w: _lib.call(
-            "ocf_corr_bwd", P(gout), P(out), P(f1), P(f2), P(d1), P(d2), B, C, h, w, 4, 0, 0, 0.1, st), 4 * n * (81 + 4 * C), 1)
+        table["corr_fwd_L%d" % lvl] = (lambda f1=f1, f2=f2, out=out, msk=msk, C=C, h=h, w=w: _lib.call(
+            "ocf_corr_fwd", P(f1), P(f2), P(out), B, C, h, w, 4, 0, 0.1, None, P(msk), st), 4 * n * (2 * C + 81) + n * 81 // 8, 2)
+        table["corr_bwd_L%d" % lvl] = (lambda gout=gout, msk=msk, f1=f1, f2=f2, d1=d1, d2=d2, C=C, h=h, w=w: _lib.call(
+            "ocf_corr_bwd", P(gout), None, P(f1), P(f2), P(d1), P(d2), B, C, h, w, 4, 0, 0, 0.1, P(msk), st), 4 * n * (81 + 4 * C) + n * 81 // 8, 1)
         # normalisation of the two feature maps of the level (3 kernels fwd, 3 kernels bwd)
         y1, y2 = torch.empty_like(f1), torch.empty_like(f2)
         stats = torch.empty(8 * 2 * B + 8, device=dev)

@@ -33,7 +33,7 @@ typedef void* ocf_stream_t; /* cudaStream_t */
 #define OCF_EUNSUPPORTED (-3) /* argument value outside what the kernels implement */
 #define OCF_EALIGN (-4)       /* pointer not aligned to 4 bytes / stride not usable */
 
-#define OCF_ABI_VERSION 1
+#define OCF_ABI_VERSION 2
 #define OCF_MAX_DISPLACEMENT 16
 
 int ocf_abi_version(void);
@@ -54,9 +54,13 @@ const char* ocf_error_string(int code);
  *   norm: optional DEVICE pointer to {mean, inv_std}; when non-NULL both inputs are normalised on the
  *   fly as (x-mean)*inv_std inside the image (normalize_features with default flags,
  *   correlation_layer.py:42-82, fused with the correlation).
+ *   mask_out: optional (d == 4, norm == NULL only) sign bitmask of the pre-activation cost volume for the backward of
+ *   the fused LeakyReLU: [B][(2d+1)^2][H][ceil(W/8)] bytes, bit p of a byte = pixel x = 8*byte + p, set when the value
+ *   is > 0.  Saving it instead of the activated output costs 1/32 of the bytes (B*81*H*ceil(W/8)).
  * ------------------------------------------------------------------------------------------- */
 int ocf_corr_fwd(const float* f1, const float* f2, float* out, int B, int C, int H, int W, int d,
-                 long long out_bstride, float leaky_slope, const float* norm, ocf_stream_t stream);
+                 long long out_bstride, float leaky_slope, const float* norm, unsigned char* mask_out,
+                 ocf_stream_t stream);
 
 /* Backward of the above (autograd of correlation_layer.py:33-39).
  *   df1[b,c,y,x] = (1/C) sum_k g'[b,k,y,x] * f2[b,c,y+dy,x+dx]
@@ -65,10 +69,12 @@ int ocf_corr_fwd(const float* f1, const float* f2, float* out, int B, int C, int
  *   forward output).  df1 or df2 may be NULL (not needed).
  *   g_bstride / act_bstride: batch strides of grad_out / out_act in elements, 0 = dense.  The gradient of a
  *   cost volume that was concatenated into a wider tensor (cost_volume_flow_net.py:176-180) arrives as a channel
- *   slice of the concat gradient: dense per batch item, wider batch stride -- it is consumed in place. */
+ *   slice of the concat gradient: dense per batch item, wider batch stride -- it is consumed in place.
+ *   mask: optional sign bitmask written by ocf_corr_fwd (d == 4); when non-NULL it replaces out_act (which may then be
+ *   NULL) as the source of LeakyReLU'. */
 int ocf_corr_bwd(const float* grad_out, const float* out_act, const float* f1, const float* f2,
                  float* df1, float* df2, int B, int C, int H, int W, int d, long long g_bstride,
-                 long long act_bstride, float leaky_slope, ocf_stream_t stream);
+                 long long act_bstride, float leaky_slope, const unsigned char* mask, ocf_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Feature normalisation.  Replaces normalize_features(feature_list, normalize, center,

@@ -19,8 +19,8 @@ c_s = ctypes.c_void_p  # cudaStream_t
 # name -> argtypes ; every entry returns int.  Must list every symbol of include/ocflow_b200.h
 # (tests/test_abi.py cross-checks this table against the header).
 SIGNATURES = {
-    "ocf_corr_fwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_ll, c_fl, c_f, c_s],
-    "ocf_corr_bwd": [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_ll, c_ll, c_fl, c_s],
+    "ocf_corr_fwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_ll, c_fl, c_f, c_f, c_s],
+    "ocf_corr_bwd": [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_ll, c_ll, c_fl, c_f, c_s],
     "ocf_normalize_fwd": [c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_s],
     "ocf_normalize_bwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_s],
     "ocf_warp_fwd": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_s],

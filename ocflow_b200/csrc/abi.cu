@@ -48,7 +48,7 @@ extern "C" int ocf_host_corr_fwd(const float* f1, const float* f2, float* out, i
   if (int e = h2d(a, f1, n)) return e;
   if (int e = h2d(b, f2, n)) return e;
   if (int e = o.alloc(no)) return e;
-  if (int e = ocf_corr_fwd(a.p, b.p, o.p, B, C, H, W, d, 0, 1.0f, nullptr, nullptr)) return e;
+  if (int e = ocf_corr_fwd(a.p, b.p, o.p, B, C, H, W, d, 0, 1.0f, nullptr, nullptr, nullptr)) return e;
   return (int)cudaMemcpy(out, o.p, no * sizeof(float), cudaMemcpyDeviceToHost);
 }
 

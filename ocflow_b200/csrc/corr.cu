@@ -216,8 +216,8 @@ __device__ __forceinline__ ChunkRange chunk_range(int C, int CC, int ksplit, int
 template <class T, int STG>
 __global__ void __maxnreg__(96)
 corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2, const float* __restrict__ f1,
-               const float* __restrict__ f2, float* __restrict__ out, int C, int H, int W, long long out_bstride, float inv_c,
-               float slope, int ksplit) {
+               const float* __restrict__ f2, float* __restrict__ out, unsigned char* __restrict__ mask, int C, int H, int W,
+               long long out_bstride, float inv_c, float slope, int ksplit) {
   constexpr int D = T::D, PX = T::PX, ND = T::ND, TH = T::TH, TW = T::TW, CC = T::CC, STAGES = T::STAGES;
   constexpr int S1 = T::S1, S2 = T::S2, F2H = T::F2H, F2W = T::F2W, WIN = T::WIN;
   constexpr int STAGE = T::F1_STAGE + T::F2_STAGE;
@@ -355,14 +355,18 @@ corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
     const int y = y0 + ty, xs = x0 + tx * PX;
     if (y >= H || xs >= W) return;
     float* ob = out + (size_t)b * bstride + ((size_t)(dyi * ND) * H + y) * W + xs;
+    const int Wb = (W + 7) >> 3;
 #pragma unroll
     for (int dx = 0; dx < ND; ++dx) {
       float r[PX];
+      unsigned mbyte = 0u;
 #pragma unroll
       for (int p = 0; p < PX; ++p) {
         const float v = acc_get(dx, p) * inv_c;
+        mbyte |= (v > 0.f ? 1u : 0u) << p;
         r[p] = v > 0.f ? v : v * slope;
       }
+      if (mask != nullptr) mask[(((size_t)b * ND * ND + dyi * ND + dx) * H + y) * Wb + (xs >> 3)] = (unsigned char)mbyte;
       float* o = ob + (size_t)dx * H * W;
       if (VEC) {  // W % 4 == 0 and 16B-aligned rows: each float4 is entirely inside or outside
 #pragma unroll
@@ -396,11 +400,16 @@ corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
   // ksplit peer reads of an item are issued together (independent DSMEM loads, ~215 cycles each)
   const unsigned rank = cluster.block_rank();
   constexpr int ROW4 = TW / 4, PLANE4 = TH * ROW4;
+  static_assert(ROW4 % 2 == 0 && T::THREADS % 2 == 0, "mask nibbles are paired across adjacent lanes");
   const int nplanes = (ND * ND - (int)rank + ksplit - 1) / ksplit;
+  const int Wb = (W + 7) >> 3;
   const float* peers[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) peers[q] = cluster.map_shared_rank(part, q < ksplit ? q : 0);
-  for (int it = tid; it < nplanes * PLANE4; it += blockDim.x) {
+  const int nitems = nplanes * PLANE4;
+  for (int it0 = 0; it0 < nitems; it0 += blockDim.x) {  // uniform trip count: every lane takes part in the shuffle below
+    const bool valid = it0 + tid < nitems;
+    const int it = valid ? it0 + tid : 0;
     const int kp = it / PLANE4, i = it - kp * PLANE4;
     const int k = (int)rank + kp * ksplit;
     const int ry = i / ROW4, x4 = i - ry * ROW4;
@@ -414,10 +423,19 @@ corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
     for (int q = 1; q < 8; ++q)
       if (q < ksplit) { s.x += v[q].x; s.y += v[q].y; s.z += v[q].z; s.w += v[q].w; }
     const int y = y0 + ry, x = x0 + x4 * 4;
-    if (y < H && x < W) {
-      float r[4] = {s.x * inv_c, s.y * inv_c, s.z * inv_c, s.w * inv_c};
+    float r[4] = {s.x * inv_c, s.y * inv_c, s.z * inv_c, s.w * inv_c};
+    unsigned nib = 0u;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) r[j] = r[j] > 0.f ? r[j] : r[j] * slope;
+    for (int j = 0; j < 4; ++j) {
+      nib |= (r[j] > 0.f ? 1u : 0u) << j;
+      r[j] = r[j] > 0.f ? r[j] : r[j] * slope;
+    }
+    // items it (even) and it + 1 are the two halves of one 8-pixel mask byte and sit in adjacent lanes of one warp
+    // (item count and loop stride are even), so the odd lane hands its nibble to the even one
+    const unsigned other = __shfl_xor_sync(0xffffffffu, nib, 1);
+    if (mask != nullptr && valid && (x4 & 1) == 0 && y < H && x < W)
+      mask[(((size_t)b * ND * ND + k) * H + y) * Wb + (x >> 3)] = (unsigned char)(nib | (other << 4));
+    if (valid && y < H && x < W) {
       float* o = out + (size_t)b * bstride + ((size_t)k * H + y) * W + x;
       if (VEC) {
         *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
@@ -438,8 +456,9 @@ corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
 // without this every tile would wait ~1.5 us for its first box with nothing else to do).
 template <class T, int UNROLL>
 __global__ void __maxnreg__(OCF_FWD_REGS)
-corr_fwd_persist(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2, float* __restrict__ out, int C,
-                 int H, int W, long long out_bstride, float inv_c, float slope, int tiles_x, int tiles_y, int ntiles) {
+corr_fwd_persist(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2, float* __restrict__ out,
+                 unsigned char* __restrict__ mask, int C, int H, int W, long long out_bstride, float inv_c, float slope, int tiles_x,
+                 int tiles_y, int ntiles) {
   constexpr int D = T::D, PX = T::PX, ND = T::ND, TH = T::TH, TW = T::TW, CC = T::CC, STAGES = T::STAGES;
   constexpr int S1 = T::S1, S2 = T::S2, F2H = T::F2H, WIN = T::WIN;
   constexpr int STAGE = T::F1_STAGE + T::F2_STAGE;
@@ -549,9 +568,11 @@ corr_fwd_persist(const __grid_constant__ CUtensorMap map1, const __grid_constant
     const int y = tyi * TH + ty, xs = txi * TW + tx * PX;
     const bool inside = y < H && xs < W;
     float* ob = out + (size_t)b * bstride + ((size_t)(dyi * ND) * H + y) * W + xs;
+    const int Wb = (W + 7) >> 3;
 #pragma unroll
     for (int dx = 0; dx < ND; ++dx) {
       float rr[PX];
+      unsigned mbyte = 0u;
 #pragma unroll
       for (int p = 0; p < PX; ++p) {
         const int first = p & 1;
@@ -564,9 +585,11 @@ corr_fwd_persist(const __grid_constant__ CUtensorMap map1, const __grid_constant
           v = ((dx - first) & 1) ? hi : lo;
         }
         v *= inv_c;
+        mbyte |= (v > 0.f ? 1u : 0u) << p;
         rr[p] = v > 0.f ? v : v * slope;
       }
       if (inside) {
+        if (mask != nullptr) mask[(((size_t)b * ND * ND + dyi * ND + dx) * H + y) * Wb + (xs >> 3)] = (unsigned char)mbyte;
         float* o = ob + (size_t)dx * H * W;
 #pragma unroll
         for (int q = 0; q < PX / 4; ++q)
@@ -629,7 +652,8 @@ template <class T, int CR, int STG>
 __global__ void __launch_bounds__(Threads<T, STG>::value, 2)
 corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
                const __grid_constant__ CUtensorMap mapg, const __grid_constant__ CUtensorMap mapa, const float* __restrict__ g,
-               const float* __restrict__ oact, const float* __restrict__ f1, const float* __restrict__ f2, float* __restrict__ df1,
+               const float* __restrict__ oact, const unsigned char* __restrict__ mask, const float* __restrict__ f1,
+               const float* __restrict__ f2, float* __restrict__ df1,
                float* __restrict__ df2, int C, int H, int W, long long g_bstride, long long a_bstride, float inv_c, float slope,
                int nmodes, int first_mode, int ksplit) {
   constexpr int D = T::D, PX = T::PX, ND = T::ND, TH = T::TH, TW = T::TW, CC = T::CC, STAGES = T::STAGES;
@@ -668,7 +692,7 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
       mbar_fence_init();
     }
     __syncthreads();
-    const bool has_act = oact != nullptr;
+    const bool has_act = oact != nullptr || mask != nullptr;
     if (dyi == ND) {
       if (lane == 0) {
         // coefficient boxes: mode 0 -> planes dy*ND.. at (y0, x0) ; mode 1 -> planes (2D-dy)*ND.. at (y0+dy-D, x0-D)
@@ -696,8 +720,29 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
     // zero-filled out-of-image element the mask value is irrelevant, so addresses are clamped instead of predicated
     // (W % 4 == 0 on this path: an aligned group of 4 is entirely inside or entirely outside the row).
     unsigned mbits[3] = {0u, 0u, 0u};  // bit (dx % 3) * PX + p of word dx / 3
-    if (has_act) {
-      static_assert(ND == 9 && PX == 8, "mask packing assumes 9 displacements x 8 pixels");
+    static_assert(ND == 9 && PX == 8, "mask packing assumes 9 displacements x 8 pixels");
+    if (mask != nullptr) {
+      // the forward's sign bitmask (1 bit per cost-volume element, 8 pixels per byte): 9 / 18 byte loads per thread
+      const int Wb = (W + 7) >> 3;
+      const unsigned char* mp = mask + (size_t)b * ND * ND * H * Wb;
+      const int xs = x0 + tx * PX;
+      if (mode == 0) {
+        const int y = min(y0 + ty, H - 1), bx = min(xs >> 3, Wb - 1);
+#pragma unroll
+        for (int dx = 0; dx < ND; ++dx)
+          mbits[dx / 3] |= (unsigned)__ldg(mp + ((size_t)(dyi * ND + dx) * H + y) * Wb + bx) << ((dx % 3) * PX);
+      } else {
+        const int sy = min(max(y0 + ty + dyi - D, 0), H - 1);
+#pragma unroll
+        for (int dx = 0; dx < ND; ++dx) {
+          const unsigned char* row = mp + ((size_t)((2 * D - dyi) * ND + (2 * D - dx)) * H + sy) * Wb;
+          const int c0 = xs + dx - D;        // first needed column (>= -D); out-of-image columns carry zero coefficients
+          const int fb = c0 >> 3;            // floor(c0 / 8), -1 at the left border
+          const unsigned lo = __ldg(row + min(max(fb, 0), Wb - 1)), hi = __ldg(row + min(fb + 1, Wb - 1));
+          mbits[dx / 3] |= (((lo | (hi << 8)) >> (c0 & 7)) & 0xffu) << ((dx % 3) * PX);
+        }
+      }
+    } else if (oact != nullptr) {
       const float* ap = oact + ab;
       const int xs = x0 + tx * PX;
       if (mode == 0) {
@@ -787,7 +832,10 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
         float v = 0.f;
         if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
           v = __ldg(g + off + sx);
-          if (oact != nullptr && !(__ldg(oact + (off - gb + ab) + sx) > 0.f)) v *= slope;
+          if (mask != nullptr) {
+            const int Wb = (W + 7) >> 3;
+            if (!((__ldg(mask + (((size_t)b * ND * ND + k) * H + sy) * Wb + (sx >> 3)) >> (sx & 7)) & 1)) v *= slope;
+          } else if (oact != nullptr && !(__ldg(oact + (off - gb + ab) + sx) > 0.f)) v *= slope;
         }
         G[dx][p] = v;
       }
@@ -997,13 +1045,15 @@ bool make_map(CUtensorMap* map, const float* base, int B, int C, int H, int W, i
 }  // namespace
 
 extern "C" int ocf_corr_fwd(const float* f1, const float* f2, float* out, int B, int C, int H, int W, int d,
-                            long long out_bstride, float leaky_slope, const float* norm, ocf_stream_t stream) {
+                            long long out_bstride, float leaky_slope, const float* norm, unsigned char* mask_out,
+                            ocf_stream_t stream) {
   OCF_REQUIRE_PTR(f1); OCF_REQUIRE_PTR(f2); OCF_REQUIRE_PTR(out);
   OCF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, OCF_ESHAPE);
   OCF_REQUIRE(d >= 0 && d <= OCF_MAX_DISPLACEMENT, OCF_EUNSUPPORTED);
   const long long nd = 2 * d + 1;
   OCF_REQUIRE(out_bstride == 0 || out_bstride >= nd * nd * H * W, OCF_ESHAPE);
   OCF_REQUIRE(B <= 8191, OCF_EUNSUPPORTED);
+  OCF_REQUIRE(mask_out == nullptr || (d == 4 && norm == nullptr), OCF_EUNSUPPORTED);  // only the tiled kernels emit the sign mask
   cudaStream_t s = ocf_cast_stream(stream);
   const float inv_c = 1.0f / (float)C;
   if (d == 4 && norm == nullptr) {
@@ -1025,15 +1075,15 @@ extern "C" int ocf_corr_fwd(const float* f1, const float* f2, float* out, int B,
       if (int e = set_smem(kernel, psmem)) return e;
       const int ntiles = gx * gy * B;
       const int nblk = ntiles < OCF_FWD_CTAS_PER_SM * OCF_SM_COUNT ? ntiles : OCF_FWD_CTAS_PER_SM * OCF_SM_COUNT;
-      if (int e = launch_kernel(kernel, dim3(nblk), TP::THREADS, psmem, s, 1, m1, m2, out, C, H, W, out_bstride, inv_c, leaky_slope, gx, gy, ntiles)) return e;
+      if (int e = launch_kernel(kernel, dim3(nblk), TP::THREADS, psmem, s, 1, m1, m2, out, mask_out, C, H, W, out_bstride, inv_c, leaky_slope, gx, gy, ntiles)) return e;
     } else if (tma) {
       auto kernel = corr_fwd_tiled<T, STG_TMA>;
       if (int e = set_smem(kernel, smem)) return e;
-      if (int e = launch_kernel(kernel, grid, T::THREADS, smem, s, ks, m1, m2, f1, f2, out, C, H, W, out_bstride, inv_c, leaky_slope, ks)) return e;
+      if (int e = launch_kernel(kernel, grid, T::THREADS, smem, s, ks, m1, m2, f1, f2, out, mask_out, C, H, W, out_bstride, inv_c, leaky_slope, ks)) return e;
     } else {
       auto kernel = vec ? corr_fwd_tiled<T, STG_ASYNC16> : corr_fwd_tiled<T, STG_ASYNC4>;
       if (int e = set_smem(kernel, smem)) return e;
-      if (int e = launch_kernel(kernel, grid, T::THREADS, smem, s, ks, m1, m2, f1, f2, out, C, H, W, out_bstride, inv_c, leaky_slope, ks)) return e;
+      if (int e = launch_kernel(kernel, grid, T::THREADS, smem, s, ks, m1, m2, f1, f2, out, mask_out, C, H, W, out_bstride, inv_c, leaky_slope, ks)) return e;
     }
   } else {
     dim3 grid((H * W + 127) / 128, (unsigned)nd, B);
@@ -1044,7 +1094,7 @@ extern "C" int ocf_corr_fwd(const float* f1, const float* f2, float* out, int B,
 
 extern "C" int ocf_corr_bwd(const float* grad_out, const float* out_act, const float* f1, const float* f2, float* df1,
                             float* df2, int B, int C, int H, int W, int d, long long g_bstride, long long act_bstride,
-                            float leaky_slope, ocf_stream_t stream) {
+                            float leaky_slope, const unsigned char* mask, ocf_stream_t stream) {
   OCF_REQUIRE_PTR(grad_out); OCF_REQUIRE_PTR(f1); OCF_REQUIRE_PTR(f2);
   OCF_REQUIRE(df1 != nullptr || df2 != nullptr, OCF_ENULL);
   OCF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, OCF_ESHAPE);
@@ -1053,6 +1103,8 @@ extern "C" int ocf_corr_bwd(const float* grad_out, const float* out_act, const f
   OCF_REQUIRE(g_bstride == 0 || g_bstride >= nd * nd * H * W, OCF_ESHAPE);
   OCF_REQUIRE(act_bstride == 0 || act_bstride >= nd * nd * H * W, OCF_ESHAPE);
   OCF_REQUIRE(B <= 4095 && C <= 65535, OCF_EUNSUPPORTED);
+  OCF_REQUIRE(mask == nullptr || d == 4, OCF_EUNSUPPORTED);
+  if (mask != nullptr) out_act = nullptr;  // the bitmask carries the same information in 1/32 of the bytes
   cudaStream_t s = ocf_cast_stream(stream);
   const float inv_c = 1.0f / (float)C;
   if (d == 4) {
@@ -1061,7 +1113,7 @@ extern "C" int ocf_corr_bwd(const float* grad_out, const float* out_act, const f
     const int nmodes = (df1 != nullptr && df2 != nullptr) ? 2 : 1;
     const int first = df1 != nullptr ? 0 : 1;
     const int gx = (W + T::TW - 1) / T::TW, gy = (H + T::TH - 1) / T::TH;
-    const int ks = pick_ksplit((long long)gx * gy * B * nmodes, C, 2 * T::CC, false, out_act != nullptr ? 30.0 : 16.0);
+    const int ks = pick_ksplit((long long)gx * gy * B * nmodes, C, 2 * T::CC, false, out_act != nullptr ? 30.0 : (mask != nullptr ? 18.0 : 16.0));
     dim3 grid(gx, gy, B * nmodes * ks);
     const bool vec = (W % 4 == 0) && ocf_aligned16(f1) && ocf_aligned16(f2) && (df1 == nullptr || ocf_aligned16(df1)) &&
                      (df2 == nullptr || ocf_aligned16(df2));
@@ -1081,12 +1133,12 @@ extern "C" int ocf_corr_bwd(const float* grad_out, const float* out_act, const f
       if (gstage > smem) smem = gstage;
       auto kernel = corr_bwd_tiled<T, BWD_CR, STG_TMA>;
       if (int e = set_smem(kernel, smem)) return e;
-      if (int e = launch_kernel(kernel, grid, T::THREADS + 32, smem, s, 1, m1, m2, mg, ma, grad_out, out_act, f1, f2, df1, df2, C, H, W, g_bstride,
+      if (int e = launch_kernel(kernel, grid, T::THREADS + 32, smem, s, 1, m1, m2, mg, ma, grad_out, out_act, mask, f1, f2, df1, df2, C, H, W, g_bstride,
                                 act_bstride, inv_c, leaky_slope, nmodes, first, ks)) return e;
     } else {
       auto kernel = vec ? corr_bwd_tiled<T, BWD_CR, STG_ASYNC16> : corr_bwd_tiled<T, BWD_CR, STG_ASYNC4>;
       if (int e = set_smem(kernel, smem)) return e;
-      if (int e = launch_kernel(kernel, grid, T::THREADS, smem, s, 1, m1, m2, mg, ma, grad_out, out_act, f1, f2, df1, df2, C, H, W, g_bstride,
+      if (int e = launch_kernel(kernel, grid, T::THREADS, smem, s, 1, m1, m2, mg, ma, grad_out, out_act, mask, f1, f2, df1, df2, C, H, W, g_bstride,
                                 act_bstride, inv_c, leaky_slope, nmodes, first, ks)) return e;
     }
   } else {

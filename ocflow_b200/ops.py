@@ -43,10 +43,17 @@ class _CostVolume(torch.autograd.Function):
         B, C, H, W = f1.shape
         nd = 2 * d + 1
         out = torch.empty((B, nd * nd, H, W), device=f1.device, dtype=torch.float32)
+        # fused LeakyReLU: the d = 4 kernels also emit the sign of every cost-volume element as a bitmask (8 pixels per
+        # byte); the backward needs nothing else, so the 81-plane output is NOT kept alive by autograd (1/32 of the bytes)
+        mask = None
+        if slope != 1.0 and d == 4:
+            mask = torch.empty((B, nd * nd, H, (W + 7) // 8), device=f1.device, dtype=torch.uint8)
         with torch.cuda.device_of(f1):
-            _lib.call("ocf_corr_fwd", _p(f1), _p(f2), _p(out), B, C, H, W, d, 0, float(slope), None, _stream())
-        ctx.d, ctx.slope = d, float(slope)
-        if slope != 1.0:
+            _lib.call("ocf_corr_fwd", _p(f1), _p(f2), _p(out), B, C, H, W, d, 0, float(slope), None, _p(mask), _stream())
+        ctx.d, ctx.slope, ctx.has_mask = d, float(slope), mask is not None
+        if mask is not None:
+            ctx.save_for_backward(f1, f2, mask)
+        elif slope != 1.0:
             ctx.save_for_backward(f1, f2, out)
         else:
             ctx.save_for_backward(f1, f2)
@@ -56,7 +63,8 @@ class _CostVolume(torch.autograd.Function):
     def backward(ctx, g):
         saved = ctx.saved_tensors
         f1, f2 = saved[0], saved[1]
-        act = saved[2] if len(saved) == 3 else None
+        act = saved[2] if len(saved) == 3 and not ctx.has_mask else None
+        mask = saved[2] if ctx.has_mask else None
         B, C, H, W = f1.shape
         # The incoming gradient is usually a channel slice of the decoder's concat gradient (CatBackward hands out
         # `narrow` views): dense per batch item, only the batch stride differs.  The C ABI takes that stride, so the
@@ -75,7 +83,7 @@ class _CostVolume(torch.autograd.Function):
         df2 = torch.empty_like(f2) if need2 else None
         if need1 or need2:
             with torch.cuda.device_of(f1):
-                _lib.call("ocf_corr_bwd", _p(g), _p(act), _p(f1), _p(f2), _p(df1), _p(df2), B, C, H, W, ctx.d, g_bstride, 0, ctx.slope, _stream())
+                _lib.call("ocf_corr_bwd", _p(g), _p(act), _p(f1), _p(f2), _p(df1), _p(df2), B, C, H, W, ctx.d, g_bstride, 0, ctx.slope, _p(mask), _stream())
         return df1, df2, None, None
 
 

@@ -26,7 +26,7 @@ def test_header_declares_and_library_exports_every_symbol():
     lib = _lib.load()
     for name in decl:
         assert hasattr(lib, name), "libocflow_b200.so does not export %s" % name
-    assert lib.ocf_abi_version() == 1
+    assert lib.ocf_abi_version() == 2
     assert lib.ocf_build_sm() == 100
     assert b"OCF_ENULL" in lib.ocf_error_string(-1)
 
@@ -47,11 +47,12 @@ def test_argument_validation_happens_before_any_launch():
 
     lib = _lib.load()
     one = ctypes.c_void_p(16)  # never dereferenced: validation fails first
-    assert lib.ocf_corr_fwd(None, one, one, 1, 1, 1, 1, 4, 0, 1.0, None, None) == -1
-    assert lib.ocf_corr_fwd(one, one, one, 0, 1, 1, 1, 4, 0, 1.0, None, None) == -2
-    assert lib.ocf_corr_fwd(one, one, one, 1, 1, 1, 1, 17, 0, 1.0, None, None) == -3
-    assert lib.ocf_corr_fwd(one, one, one, 1, 1, 2, 2, 4, 5, 1.0, None, None) == -2  # out_bstride too small
-    assert lib.ocf_corr_bwd(one, None, one, one, None, None, 1, 1, 1, 1, 4, 0, 0, 1.0, None) == -1
+    assert lib.ocf_corr_fwd(None, one, one, 1, 1, 1, 1, 4, 0, 1.0, None, None, None) == -1
+    assert lib.ocf_corr_fwd(one, one, one, 0, 1, 1, 1, 4, 0, 1.0, None, None, None) == -2
+    assert lib.ocf_corr_fwd(one, one, one, 1, 1, 1, 1, 17, 0, 1.0, None, None, None) == -3
+    assert lib.ocf_corr_fwd(one, one, one, 1, 1, 1, 1, 2, 0, 1.0, None, one, None) == -3   # sign mask only from the d = 4 kernels
+    assert lib.ocf_corr_fwd(one, one, one, 1, 1, 2, 2, 4, 5, 1.0, None, None, None) == -2  # out_bstride too small
+    assert lib.ocf_corr_bwd(one, None, one, one, None, None, 1, 1, 1, 1, 4, 0, 0, 1.0, None, None) == -1
     assert lib.ocf_warp_fwd(one, one, None, one, 1, 1, 1, 1, 8, 1.0, None) == -3
     assert lib.ocf_warp_bwd(one, one, one, None, None, None, None, 1, 1, 1, 1, 0, 1.0, None) == -1
     assert lib.ocf_range_map(one, None, None, 1, 1, 1, None) == -1

@@ -216,7 +216,7 @@ def test_cuda_rejects_cpu_and_bad_args():
         ocf.warp(torch.zeros(1, 2, 3, 3, device="cuda", dtype=torch.float64), torch.zeros(1, 2, 3, 3, device="cuda"))
     with pytest.raises(RuntimeError):
         ocf.compute_cost_volume(torch.zeros(1, 2, 3, 3, device="cuda"), torch.zeros(1, 2, 3, 3, device="cuda"), 17)
-    assert _lib.load().ocf_corr_fwd(None, None, None, 1, 1, 1, 1, 4, 0, 1.0, None, None) == -1
+    assert _lib.load().ocf_corr_fwd(None, None, None, 1, 1, 1, 1, 4, 0, 1.0, None, None, None) == -1
 
 
 @pytest.mark.parametrize("shape", [(2, 32, 24, 32), (1, 16, 9, 13)])

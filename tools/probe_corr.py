@@ -47,16 +47,19 @@ def timeit(fn):
 
 
 print("geometry B=%d %dx%d" % (B, h, w))
-print("%5s %10s %10s %10s %10s %10s" % ("C", "fwd", "bwd+act", "bwd", "bwd_df1", "bwd_df2"))
+print("%5s %10s %10s %10s %10s %10s %10s %10s" % ("C", "fwd+mask", "fwd", "bwd+act", "bwd+mask", "bwd", "bwd_df1", "bwd_df2"))
 for C in (int(v) for v in a.channels.split(",")):
     f1 = torch.randn(B, C, h, w, device=dev)
     f2 = torch.randn(B, C, h, w, device=dev)
     out = torch.empty(B, 81, h, w, device=dev)
     g = torch.randn(B, 81, h, w, device=dev)
+    msk = torch.zeros(B, 81, h, (w + 7) // 8, device=dev, dtype=torch.uint8)
     d1, d2 = torch.empty_like(f1), torch.empty_like(f2)
-    t_f = timeit(lambda: _lib.call("ocf_corr_fwd", P(f1), P(f2), P(out), B, C, h, w, 4, 0, 0.1, None, st))
-    t_ba = timeit(lambda: _lib.call("ocf_corr_bwd", P(g), P(out), P(f1), P(f2), P(d1), P(d2), B, C, h, w, 4, 0, 0, 0.1, st))
-    t_b = timeit(lambda: _lib.call("ocf_corr_bwd", P(g), None, P(f1), P(f2), P(d1), P(d2), B, C, h, w, 4, 0, 0, 1.0, st))
-    t_b1 = timeit(lambda: _lib.call("ocf_corr_bwd", P(g), None, P(f1), P(f2), P(d1), None, B, C, h, w, 4, 0, 0, 1.0, st))
-    t_b2 = timeit(lambda: _lib.call("ocf_corr_bwd", P(g), None, P(f1), P(f2), None, P(d2), B, C, h, w, 4, 0, 0, 1.0, st))
-    print("%5d %10.2f %10.2f %10.2f %10.2f %10.2f" % (C, t_f, t_ba, t_b, t_b1, t_b2))
+    t_f = timeit(lambda: _lib.call("ocf_corr_fwd", P(f1), P(f2), P(out), B, C, h, w, 4, 0, 0.1, None, P(msk), st))
+    t_fn = timeit(lambda: _lib.call("ocf_corr_fwd", P(f1), P(f2), P(out), B, C, h, w, 4, 0, 0.1, None, None, st))
+    t_ba = timeit(lambda: _lib.call("ocf_corr_bwd", P(g), P(out), P(f1), P(f2), P(d1), P(d2), B, C, h, w, 4, 0, 0, 0.1, None, st))
+    t_bm = timeit(lambda: _lib.call("ocf_corr_bwd", P(g), None, P(f1), P(f2), P(d1), P(d2), B, C, h, w, 4, 0, 0, 0.1, P(msk), st))
+    t_b = timeit(lambda: _lib.call("ocf_corr_bwd", P(g), None, P(f1), P(f2), P(d1), P(d2), B, C, h, w, 4, 0, 0, 1.0, None, st))
+    t_b1 = timeit(lambda: _lib.call("ocf_corr_bwd", P(g), None, P(f1), P(f2), P(d1), None, B, C, h, w, 4, 0, 0, 1.0, None, st))
+    t_b2 = timeit(lambda: _lib.call("ocf_corr_bwd", P(g), None, P(f1), P(f2), None, P(d2), B, C, h, w, 4, 0, 0, 1.0, None, st))
+    print("%5d %10.2f %10.2f %10.2f %10.2f %10.2f %10.2f %10.2f" % (C, t_f, t_fn, t_ba, t_bm, t_b, t_b1, t_b2))
