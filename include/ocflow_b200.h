@@ -218,6 +218,18 @@ int ocf_census_bwd(const float* pred, const float* img, const float* occ, const 
                    int H, int W, int max_distance, ocf_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * End-point-error metrics.  Replaces flow_error (models/data/utils/flow_utils.py:179-232) and
+ *   flow_kitti_error (:234-271), which the reference evaluates in numpy on the host.  gt, pred: [B,2,H,W].
+ *   kitti == 0: pixels whose ground truth exceeds 1e7 in magnitude are zeroed in all maps (:201-206) and still counted;
+ *               sums[0] = sum of end-point errors, sums[1] = number of pixels.
+ *   kitti == 1: only pixels with mask != 0 count (mask [B,1,H,W], NULL = all); sums[2] = number of outliers
+ *               (epe > 3 and epe / (|gt| + 1e-5) > 0.05, :258-264).
+ *   sums: 3 doubles on the device, zeroed inside.
+ * ------------------------------------------------------------------------------------------- */
+int ocf_flow_metrics(const float* gt, const float* pred, const float* mask, double* sums, int B, int H, int W, int kitti,
+                     ocf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host-buffer convenience entry points (HOST pointers; allocate, copy in, run, copy out, free,
  * synchronise).  They exist so the C ABI can be exercised end-to-end without any Python/torch.
  * ------------------------------------------------------------------------------------------- */

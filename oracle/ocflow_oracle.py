@@ -288,6 +288,29 @@ def ssim(img1, img2, window_size=11, size_average=True):
 
 
 # --------------------------------------------------------------------------------------------
+# evaluation metrics                                models/data/utils/flow_utils.py:179-310
+# --------------------------------------------------------------------------------------------
+
+
+def flow_error(tu, tv, u, v):
+    """Average end-point error (flow_utils.py:179-232, occ=None): ground truth above 1e7 in magnitude marks unknown
+    pixels, which are zeroed in all four maps (so they contribute 0 and still count in the mean)."""
+    unknown = (tu.abs() > 1e7) | (tv.abs() > 1e7)
+    du = torch.where(unknown, torch.zeros_like(tu), tu - u)
+    dv = torch.where(unknown, torch.zeros_like(tv), tv - v)
+    return torch.sqrt(du * du + dv * dv).mean()
+
+
+def flow_kitti_error(tu, tv, u, v, mask):
+    """(mean EPE over mask != 0, 1 - outlier ratio) with outlier = epe > 3 and epe/(|gt|+1e-5) > 0.05 (flow_utils.py:234-271)."""
+    valid = mask != 0
+    epe = torch.sqrt((tu - u) ** 2 + (tv - v) ** 2)[valid]
+    mag = (torch.sqrt(tu ** 2 + tv ** 2) + 1e-5)[valid]
+    err = (epe > 3) & (epe / mag > 0.05)
+    return epe.mean(), 1.0 - err.sum().to(epe.dtype) / valid.sum().to(epe.dtype)
+
+
+# --------------------------------------------------------------------------------------------
 # census (ternary) photometric term -- PARITY UNPINNED
 #   BASELINE.json's north_star names a census term, but the reference defines none (SURVEY.md section 8a-14:
 #   "census: absent").  This restates the published soft census / ternary loss of UnFlow (Meister et al., AAAI 2018)
