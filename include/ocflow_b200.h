@@ -230,6 +230,16 @@ int ocf_flow_metrics(const float* gt, const float* pred, const float* mask, doub
                      ocf_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * On-device input pipeline.  Replaces, per sample, the host chain StaticCenterCrop
+ *   (models/data/datasets.py:50-55, :164-166, :182) -> ToTensor -> Normalize(0.5, 0.5) (models/lightning_datamodule.py:20-23)
+ *   -> cat(img1, img2) (datasets.py:179) and flow.transpose(2,0,1) (:185).
+ *   img1, img2: [B,H0,W0,3] uint8 (HWC, as decoded); flow_hw2: optional [B,H0,W0,2] fp32; crop origin (y0, x0), size HxW.
+ *   imgs: [B,6,H,W] fp32 = (v/255 - 0.5)/0.5 in torchvision's op order; flow: [B,2,H,W].
+ * ------------------------------------------------------------------------------------------- */
+int ocf_pack_pairs(const unsigned char* img1, const unsigned char* img2, const float* flow_hw2, float* imgs, float* flow,
+                   int B, int H0, int W0, int H, int W, int y0, int x0, ocf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host-buffer convenience entry points (HOST pointers; allocate, copy in, run, copy out, free,
  * synchronise).  They exist so the C ABI can be exercised end-to-end without any Python/torch.
  * ------------------------------------------------------------------------------------------- */

@@ -14,7 +14,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libocflow_b200.so")
 STAMP = os.path.join(PKG, ".libocflow_b200.stamp")
-SOURCES = ["corr.cu", "warp.cu", "loss.cu", "normalize.cu", "ssim.cu", "census.cu", "metrics.cu", "abi.cu"]
+SOURCES = ["corr.cu", "warp.cu", "loss.cu", "normalize.cu", "ssim.cu", "census.cu", "metrics.cu", "pack.cu", "abi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-DOCF_BUILD_SM=100",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -288,6 +288,28 @@ def ssim(img1, img2, window_size=11, size_average=True):
 
 
 # --------------------------------------------------------------------------------------------
+# input pipeline        models/data/datasets.py:50-55,157-187 + models/lightning_datamodule.py:20-23
+# --------------------------------------------------------------------------------------------
+
+
+def pack_pairs(img1_u8, img2_u8, flow_hw2=None):
+    """uint8 [B,H0,W0,3] frames (+ [B,H0,W0,2] flow) -> ([B,6,H,W] in [-1,1], [B,2,H,W]): centre crop to the largest
+    multiple of 64 (datasets.py:148-150, StaticCenterCrop :50-55), ToTensor (/255), Normalize(0.5, 0.5)
+    (lightning_datamodule.py:20-23), cat of the two frames (:179), flow transposed (:185)."""
+    B, H0, W0, _ = img1_u8.shape
+    th, tw = (H0 // 64) * 64, (W0 // 64) * 64
+    ya, yb, xa, xb = (H0 - th) // 2, (H0 + th) // 2, (W0 - tw) // 2, (W0 + tw) // 2
+
+    def prep(u8):
+        t = u8[:, ya:yb, xa:xb].permute(0, 3, 1, 2).to(torch.float32) / 255.0
+        return (t - 0.5) / 0.5
+
+    imgs = torch.cat((prep(img1_u8), prep(img2_u8)), dim=1)
+    flow = None if flow_hw2 is None else flow_hw2[:, ya:yb, xa:xb].permute(0, 3, 1, 2).contiguous()
+    return imgs, flow
+
+
+# --------------------------------------------------------------------------------------------
 # evaluation metrics                                models/data/utils/flow_utils.py:179-310
 # --------------------------------------------------------------------------------------------
 

@@ -3,4 +3,4 @@
 name=$1; shift
 mkdir -p tools/bin
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -DOCF_BUILD_SM=100 -Xcompiler -fPIC -shared "$@" \
-  -o tools/bin/lib_$name.so ocflow_b200/csrc/{corr,warp,loss,normalize,ssim,abi}.cu 2>&1 | grep -E "error" 
+  -o tools/bin/lib_$name.so ocflow_b200/csrc/{corr,warp,loss,normalize,ssim,census,metrics,abi}.cu 2>&1 | grep -E "error" 
