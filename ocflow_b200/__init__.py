@@ -12,6 +12,7 @@ Python mirror of the reference's hot-path symbols over ha
     metrics             flow_error, evaluate_flow, flow_kitti_error, evaluate_kitti_flow (models/data/utils/flow_utils.py)
     data                pack_pairs: uint8 frames (+ flow) -> cropped, normalised [B,6,H,W] on the device (datasets.py / datamodule)
     flow_net_cv         FlowNetCV (state_dict compatible with the reference network)
+    flow_model          FlowModel (models/flow_model.py, model='pwc': BASELINE config 1)
     flow_stage          FlowStageModel (general_step / general_step_occ / general_step_occ_aware / training_step)
     patch               patch_reference(): rebinds the reference's own symbols to this package
 """
