@@ -986,7 +986,11 @@ int pick_ksplit(long long tiles, int C, int min_ch, bool fwd, double prologue) {
   double best_cost = 1e30;
   for (int ks = 1; ks <= 8; ks *= 2) {
     if (ks > 1 && C / ks < min_ch) break;
-    const long long rounds = (tiles * ks + slots - 1) / slots;
+    // measured (brute-force sweep over ks at every pyramid level): 8-wide clusters stop paying once there are more than
+    // ~100 CTAs of them -- L5 (16 tiles): ks = 8 -> 128 CTAs 22.5 us, ks = 4 -> 64 CTAs 18.4 us; L6 (8 tiles): ks = 8 -> 64 CTAs
+    // 18.4 us, ks = 4 -> 24.6 us -- so the forward counts only 96 placement slots for them
+    const long long eff_slots = (fwd && ks == 8) ? 96 : slots;
+    const long long rounds = (tiles * ks + eff_slots - 1) / eff_slots;
     const double per_cta = prologue + (double)((C + ks - 1) / ks);
     const double cost = (double)rounds * per_cta + ((ks > 1 && fwd) ? 0.6 * C : 0.0);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = ks; }
