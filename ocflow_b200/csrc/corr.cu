@@ -651,7 +651,7 @@ corr_fwd_generic(const float* __restrict__ f1, const float* __restrict__ f2, flo
 template <class T, int CR, int STG>
 __global__ void __launch_bounds__(Threads<T, STG>::value, 2)
 corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
-               const __grid_constant__ CUtensorMap mapg, const __grid_constant__ CUtensorMap mapa, const float* __restrict__ g,
+               const __grid_constant__ CUtensorMap mapg, const float* __restrict__ g,
                const float* __restrict__ oact, const unsigned char* __restrict__ mask, const float* __restrict__ f1,
                const float* __restrict__ f2, float* __restrict__ df1,
                float* __restrict__ df2, int C, int H, int W, long long g_bstride, long long a_bstride, float inv_c, float slope,
@@ -1121,28 +1121,26 @@ extern "C" int ocf_corr_bwd(const float* grad_out, const float* out_act, const f
     dim3 grid(gx, gy, B * nmodes * ks);
     const bool vec = (W % 4 == 0) && ocf_aligned16(f1) && ocf_aligned16(f2) && (df1 == nullptr || ocf_aligned16(df1)) &&
                      (df2 == nullptr || ocf_aligned16(df2));
-    CUtensorMap m1, m2, mg, ma;
+    CUtensorMap m1, m2, mg;
     memset(&m1, 0, sizeof(m1));
     memset(&m2, 0, sizeof(m2));
     memset(&mg, 0, sizeof(mg));
-    memset(&ma, 0, sizeof(ma));
     const long long gbs = g_bstride ? g_bstride : nd * nd * H * W;
     const long long abs_ = act_bstride ? act_bstride : nd * nd * H * W;
     bool tma = vec && ocf_aligned16(grad_out) && (out_act == nullptr || ocf_aligned16(out_act)) && (gbs % 4 == 0) && (abs_ % 4 == 0);
     tma = tma && make_map(&m1, f1, B, C, H, W, T::S2, T::F2H, T::CC) && make_map(&m2, f2, B, C, H, W, T::S2, T::F2H, T::CC) &&
-          make_map(&mg, grad_out, B, (int)(nd * nd), H, W, T::S2, T::TH, T::ND, gbs) &&
-          (out_act == nullptr || make_map(&ma, out_act, B, (int)(nd * nd), H, W, T::S2, T::TH, T::ND, abs_));
+          make_map(&mg, grad_out, B, (int)(nd * nd), H, W, T::S2, T::TH, T::ND, gbs);
     if (tma) {
       const size_t gstage = sizeof(float) * T::ND * T::ND * T::TH * T::S2;  // coefficient staging, reused by ring + red
       if (gstage > smem) smem = gstage;
       auto kernel = corr_bwd_tiled<T, BWD_CR, STG_TMA>;
       if (int e = set_smem(kernel, smem)) return e;
-      if (int e = launch_kernel(kernel, grid, T::THREADS + 32, smem, s, 1, m1, m2, mg, ma, grad_out, out_act, mask, f1, f2, df1, df2, C, H, W, g_bstride,
+      if (int e = launch_kernel(kernel, grid, T::THREADS + 32, smem, s, 1, m1, m2, mg, grad_out, out_act, mask, f1, f2, df1, df2, C, H, W, g_bstride,
                                 act_bstride, inv_c, leaky_slope, nmodes, first, ks)) return e;
     } else {
       auto kernel = vec ? corr_bwd_tiled<T, BWD_CR, STG_ASYNC16> : corr_bwd_tiled<T, BWD_CR, STG_ASYNC4>;
       if (int e = set_smem(kernel, smem)) return e;
-      if (int e = launch_kernel(kernel, grid, T::THREADS, smem, s, 1, m1, m2, mg, ma, grad_out, out_act, mask, f1, f2, df1, df2, C, H, W, g_bstride,
+      if (int e = launch_kernel(kernel, grid, T::THREADS, smem, s, 1, m1, m2, mg, grad_out, out_act, mask, f1, f2, df1, df2, C, H, W, g_bstride,
                                 act_bstride, inv_c, leaky_slope, nmodes, first, ks)) return e;
     }
   } else {

@@ -16,9 +16,16 @@ def test_ops_refuse_cpu_and_wrong_dtype():
     for fn in (lambda: ocf.compute_cost_volume(x, x), lambda: ocf.normalize_features([x, x]), lambda: ocf.warp(x, x),
                lambda: ocf.network_warp(x, x), lambda: ocf.compute_range_map(x), lambda: ocf.photometric_error(x, x),
                lambda: ocf.robust_l1(x), lambda: ocf.first_order_smoothness_loss(x, x), lambda: ocf.gradient(x),
-               lambda: ocf.flow_mse_loss(x, x), lambda: ocf.CostVolumeLayer()(x, x)):
+               lambda: ocf.flow_mse_loss(x, x), lambda: ocf.CostVolumeLayer()(x, x),
+               lambda: ocf.census_loss(x, x), lambda: ocf.ssim(x, x), lambda: ocf.metrics.batch_epe(x, x),
+               lambda: ocf.metrics.evaluate_flow(torch.zeros(4, 4, 2), torch.zeros(4, 4, 2)),
+               lambda: ocf.data.pack_pairs(torch.zeros(1, 4, 4, 3, dtype=torch.uint8), torch.zeros(1, 4, 4, 3, dtype=torch.uint8))):
         with pytest.raises(TypeError, match="no CPU path"):
             fn()
+    # the whole-network mirrors end up in the same ops: a CPU model cannot silently run anywhere else
+    from ocflow_b200.flow_model import FlowModel
+    with pytest.raises(TypeError, match="no CPU path"):
+        FlowModel({"model": "pwc", "learning_rate": 1e-3})(torch.zeros(1, 6, 64, 64))
 
 
 def test_flownetcv_state_dict_matches_reference_shapes():
