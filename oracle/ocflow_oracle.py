@@ -1,8 +1,8 @@
 """TEST INFRASTRUCTURE ONLY -- CPU restatement of the OCFlow hot path (the parity oracle).
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference`` legs
-may import this file; the product package ``ocflow_b200`` never does (tests/test_no_oracle_leak.py
-enforces it).  Everything here is plain, dtype-generic PyTorch on the CPU -- the reference's algorithm
+may import this file; the product package ``ocflow_b200`` never does
+(tests/test_host_logic.py::test_product_never_imports_oracle_or_falls_back enforces it).  Everything here is plain, dtype-generic PyTorch on the CPU -- the reference's algorithm
 is floating-point tensor math whose arithmetic lives in ATen, so a torch restatement (fp32 for the
 parity bar, fp64 as tie-breaker) is the natural oracle; nothing here calls ``F.grid_sample``,
 ``scatter_add_`` on nonzero masks, or any reference code.
