@@ -35,13 +35,30 @@ def _try_import(name):
         return None
 
 
+_UNDO = []  # (object, attribute, original value) of every rebinding made by patch_reference(), newest last
+
+
+def unpatch_reference():
+    """Restore every symbol patch_reference() rebound (the injected cost_volume_net module stays: the reference has none).
+    Returns the number of restored attributes."""
+    n = len(_UNDO)
+    while _UNDO:
+        obj, attr, orig = _UNDO.pop()
+        setattr(obj, attr, orig)
+    return n
+
+
 def patch_reference(verbose=False):
-    """Rebind every hot-path symbol of the already-importable reference modules.  Returns the list of patched names."""
+    """Rebind every hot-path symbol of the already-importable reference modules.  Returns the list of patched names;
+    unpatch_reference() undoes it."""
     install_cost_volume_net()
     done = []
 
     def setp(obj, attr, value):
         if obj is not None and hasattr(obj, attr):
+            orig = obj.__dict__[attr] if attr in getattr(obj, "__dict__", {}) else getattr(obj, attr)
+            if orig is not value:
+                _UNDO.append((obj, attr, orig))
             setattr(obj, attr, value)
             done.append("%s.%s" % (getattr(obj, "__name__", repr(obj)), attr))
 

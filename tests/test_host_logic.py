@@ -79,16 +79,9 @@ def test_patch_reference_rebinds_every_patch_point():
     import ocflow_b200.patch as P
     from ocflow_b200 import correlation_layer, losses, warping
 
-    saved = {}
-    mods = ["models.networks.correlation_layer", "models.networks.cost_volume_flow_net", "models.networks.pwc_net", "models.model",
-            "models.flow_model", "utils"]
     import sys
-    for mn in mods:
-        m = importlib.import_module(mn)
-        saved[mn] = dict(vars(m))
-    cls_saved = {}
-    for cls in (R.cost_volume_flow_net.FlowNetCV, R.model.FlowStageModel, R.flow_model.FlowModel, R.model.TwoStageModel):
-        cls_saved[cls] = {k: cls.__dict__[k] for k in ("warp", "flow_to_warp", "compute_range_map") if k in cls.__dict__}
+    orig_ccv = R.correlation_layer.compute_cost_volume
+    orig_ssim = R.ssim.ssim
     try:
         done = P.patch_reference()
         assert R.cost_volume_flow_net.compute_cost_volume is correlation_layer.compute_cost_volume
@@ -106,13 +99,13 @@ def test_patch_reference_rebinds_every_patch_point():
         # a freshly constructed reference net now captures our normalize_features (cost_volume_flow_net.py:49)
         assert R.cost_volume_flow_net.FlowNetCV().normalize is correlation_layer.normalize_features
     finally:
-        for mn, d in saved.items():
-            m = sys.modules[mn]
-            for k, v in d.items():
-                setattr(m, k, v)
-        for cls, d in cls_saved.items():
-            for k, v in d.items():
-                setattr(cls, k, v)
+        assert P.unpatch_reference() >= 25
+    # everything is back: the reference's own functions again (other tests run the real reference after this one)
+    assert R.correlation_layer.compute_cost_volume is orig_ccv and R.cost_volume_flow_net.compute_cost_volume is orig_ccv
+    assert R.ssim.ssim is orig_ssim
+    assert R.model.photometric_error is not losses.photometric_error
+    assert R.cost_volume_flow_net.FlowNetCV.warp is not warping.network_warp_method
+    assert P.unpatch_reference() == 0
 
 
 def test_product_never_imports_oracle_or_falls_back():
