@@ -11,6 +11,7 @@ Python mirror of the reference's hot-path symbols over ha
                         ssim / SSIM (inpainting_metrics/ssim/ssim.py), census_loss (no upstream definition)
     metrics             flow_error, evaluate_flow, flow_kitti_error, evaluate_kitti_flow (models/data/utils/flow_utils.py)
     data                pack_pairs: uint8 frames (+ flow) -> cropped, normalised [B,6,H,W] on the device (datasets.py / datamodule)
+    flow_io             read_flow, save_flow (.flo files, models/data/utils/flow_utils.py)
     flow_net_cv         FlowNetCV (state_dict compatible with the reference network)
     flow_model          FlowModel (models/flow_model.py, model='pwc': BASELINE config 1)
     flow_stage          FlowStageModel (general_step / general_step_occ / general_step_occ_aware / training_step)
@@ -24,6 +25,6 @@ from .losses import (robust_l1, photometric_error, PhotometricLoss, charbonnier_
                      first_order_smoothness_loss, second_order_smoothness_loss, flow_mse_loss, flow_l1_loss,
                      occlusion_bce_loss, occlusion_focal_loss, ssim, SSIM, ssim_photometric_loss, census_loss)
 
-from . import data, metrics  # noqa: F401,E402
+from . import data, flow_io, metrics  # noqa: F401,E402
 
 __version__ = "0.1.0"
