@@ -181,7 +181,7 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------------------
 def kernel_table(args, torch):
     """name -> (callable launching exactly that kernel, algorithmic bytes, launches per training step)."""
-    from ocflow_b200 import _lib, ops
+    from ocflow_b200 import _lib
     import ctypes
 
     B, H, W = args.batch, args.height, args.width

@@ -6,8 +6,6 @@ order; inputs are CUDA tensors in the reference's layouts ([H,W] maps, [H,W,2|3]
 Deviation: `flow_error(..., occ=...)` of the reference cannot run on 2-D maps as written (it indexes the [H,W] error map
 with a flattened mask, flow_utils.py:227-230); `occ` is honoured here with the evident intent (mean over occ == 0).
 """
-import ctypes
-
 import torch
 
 from . import _lib

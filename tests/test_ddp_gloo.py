@@ -4,7 +4,6 @@ identical parameters.  (The hot-path kernels need a GPU; the driver logic does n
 import os
 import socket
 
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp

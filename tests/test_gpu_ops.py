@@ -8,7 +8,7 @@ import os
 import pytest
 import torch
 
-from conftest import GOLD, assert_close, assert_scalar_close, golden_op_files, load_golden
+from conftest import assert_close, assert_scalar_close, golden_op_files, load_golden
 from oracle import ocflow_oracle as O
 
 pytestmark = pytest.mark.gpu
