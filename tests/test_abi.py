@@ -68,3 +68,37 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libocflow_b200.so")
     with pytest.raises(RuntimeError, match="no fallback"):
         _lib.load()
+
+
+def test_header_is_plain_c_and_links_from_a_c_program(tmp_path):
+    """The boundary is a C ABI: the header must compile as C (not only C++), and a C program must link against the shared
+    library and get the documented error codes back -- without touching a GPU."""
+    import shutil
+    import subprocess
+
+    from ocflow_b200 import _lib
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi_smoke.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "ocflow_b200.h"\n'
+        "int main(void) {\n"
+        "  float x[4] = {0};\n"
+        "  if (ocf_abi_version() != OCF_ABI_VERSION) return 1;\n"
+        "  if (ocf_build_sm() != 100) return 2;\n"
+        "  if (ocf_corr_fwd(0, x, x, 1, 1, 1, 1, 4, 0, 1.0f, 0, 0, 0) != OCF_ENULL) return 3;\n"
+        "  if (ocf_corr_fwd(x, x, x, 1, 1, 1, 1, 99, 0, 1.0f, 0, 0, 0) != OCF_EUNSUPPORTED) return 4;\n"
+        "  if (ocf_warp_fwd(x, x, 0, x, 1, 1, 0, 1, 0, 1.0f, 0) != OCF_ESHAPE) return 5;\n"
+        "  if (ocf_flow_metrics(x, x, x, 0, 1, 1, 1, 0, 0) != OCF_ENULL) return 6;\n"
+        "  if (ocf_pack_pairs(0, 0, 0, 0, 0, 1, 4, 4, 4, 4, 0, 0, 0) != OCF_ENULL) return 7;\n"
+        '  if (strstr(ocf_error_string(OCF_ESHAPE), "OCF_ESHAPE") == 0) return 8;\n'
+        '  printf("abi ok\\n");\n  return 0;\n}\n')
+    exe = tmp_path / "abi_smoke"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cc = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                         "-L", libdir, "-locflow_b200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0 and "abi ok" in run.stdout, (run.returncode, run.stdout, run.stderr)
