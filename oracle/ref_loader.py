@@ -1,9 +1,9 @@
 """TEST INFRASTRUCTURE ONLY -- loader for the real OCFlow reference (never shipped, never on the product path).
 
-Imports the unmodified reference from ``$OCFLOW_REF`` or ``/root/reference`` so that
-``oracle/make_golden.py`` and the "oracle vs real reference" pin tests can call the reference's own
-functions.  The reference tree does not exist on the GPU box; everything that runs there uses the
-committed fixtures under ``tests/golden/`` instead.
+Imports the unmodified reference from ``$OCFLOW_REF``, ``baseline/_ref`` (the git-ignored install made by
+``oracle/install_ref.py``; it travels to the GPU box with the snapshot) or ``/root/reference`` (build container
+only) so that ``oracle/make_golden.py``, the "oracle vs real reference" pin tests, the patched-vs-unpatched GPU
+tests and ``bench.py --impl reference`` can call the reference's own functions.
 
 Two third-party modules the reference imports are absent from this image (and from the offline
 wheelhouse): ``pytorch_lightning`` and ``matplotlib``.  They are replaced by 2 inert stubs
@@ -14,7 +14,8 @@ import os
 import sys
 import types
 
-_CANDIDATES = (os.environ.get("OCFLOW_REF"), "/root/reference")
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CANDIDATES = (os.environ.get("OCFLOW_REF"), os.path.join(_ROOT, "baseline", "_ref"), "/root/reference")
 
 
 def reference_root():
@@ -80,6 +81,7 @@ def load():
     ref.correlation_layer = importlib.import_module("models.networks.correlation_layer")
     ref.cost_volume_flow_net = importlib.import_module("models.networks.cost_volume_flow_net")
     ref.pwc_net = importlib.import_module("models.networks.pwc_net")
+    ref.flow_net = importlib.import_module("models.networks.flow_net")
     ref.model = importlib.import_module("models.model")
     ref.flow_model = importlib.import_module("models.flow_model")
     ref.utils = importlib.import_module("utils")

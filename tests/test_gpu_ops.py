@@ -117,6 +117,8 @@ SHAPES = [
     # B, C, H, W, flow scale   (pyramid levels of config 2, KITTI/Sintel odd widths, tiny and ragged cases)
     (2, 32, 24, 32, 2.0), (1, 196, 6, 8, 1.0), (2, 16, 47, 39, 3.0), (1, 3, 33, 65, 6.0), (2, 64, 12, 20, 1.5),
     (1, 1, 1, 1, 0.5), (1, 5, 2, 3, 1.0), (1, 96, 9, 311, 2.0), (3, 128, 12, 16, 1.0), (1, 17, 8, 36, 40.0),
+    # BASELINE.json shapes in full: config-2 level L2 (B=8, C=32, 96x128) and a KITTI level of config 5 (B=4, C=16, 188x621)
+    (8, 32, 96, 128, 2.0), (4, 16, 188, 621, 2.0),
 ]
 
 
