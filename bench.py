@@ -13,10 +13,11 @@ batch (8 pairs of 384x512 per GPU).  Prints ONE JSON line 
             the loss inside the timed region, every step
   roofline  the dominant hot-path kernel of the step, timed alone on the step's own shapes with an L2 flush between
             launches: algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json
-  cpu_baseline  the CPU oracle port of the same step on the host cores (bounded sample), rank 0, N=1 only
+  cpu_baseline  the reference's own step on the host cores (bounded sample), rank 0, N=1 only
 
---impl reference times the reference's CPU algorithm (the oracle port: the reference is Python and cannot travel to
-the GPU box) on the host cores and prints the same line with "impl": "reference".
+--impl reference times the UNMODIFIED reference (installed into the git-ignored baseline/_ref by oracle/install_ref.py,
+so it travels to the GPU box) on the host cores -- same batch, shape, warm-up and steps -- and prints the same line with
+"impl": "reference".
 """
 import argparse
 import json
@@ -53,9 +54,9 @@ def parse():
     ap.add_argument("--graph", type=int, default=1, help="capture the whole step in a CUDA graph (1) or run eagerly (0)")
     ap.add_argument("--tf32", type=int, default=0, help="allow TF32 cuDNN convolutions (torch's default); 0 = strict fp32")
     ap.add_argument("--channels-last", type=int, default=0, help="experiment: keep the conv stacks in NHWC (cuDNN channels_last kernels)")
-    ap.add_argument("--cpu-sample-batch", type=int, default=2)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-roofline", action="store_true")
+    ap.add_argument("--skip-refgpu", action="store_true", help="skip the reference-on-the-B200 legs (N=1 only)")
     ap.add_argument("--skip-alt", action="store_true", help="skip the informational TF32-convolution leg (N=1 only)")
     ap.add_argument("--kernels-only", action="store_true", help="only time the hot-path kernels alone (developer aid)")
     ap.add_argument("--cuda-profiler-range", action="store_true",
@@ -118,60 +119,90 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the same step on the host cores
+# Reference arm: the UNMODIFIED reference (baseline/_ref, installed by oracle/install_ref.py) on the host cores
 # ------------------------------------------------------------------------------------------------------------
-def cpu_step_runner(batch_size, height, width):
-    """Returns (run_one_step, cores): one occ-aware step fwd+bwd+Adam of the oracle port on the CPU."""
+REF_HPARAMS = {"model": "pwc", "occ_aware": True, "photo_weight": 4.0, "smooth1_weight": 0.5, "smooth2_weight": 0.0,
+               "displacement": 4, "learning_rate": 1e-5}   # config/unsupervised_config.yml:11,23-26,31
+
+
+def reference_step_runner(batch_size, height, width, device="cpu"):
+    """(run_one_step, threads, kind): one occlusion-aware training step of the reference's own code --
+    FlowStageModel('pwc', occ_aware).general_step_occ_aware + weighted loss (models/model.py:366-409,424) + backward + Adam
+    (models/model.py:508-509) -- through the reference's public API.  Falls back to the oracle port (kind "port") only when
+    no reference tree is installed."""
     import torch
-    from oracle import ocflow_oracle as O
-    from ocflow_b200.flow_net_cv import FlowNetCV   # only for parameter shapes / the reference's default init
-    from ocflow_b200.train import DEFAULT_HPARAMS
 
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    net = FlowNetCV(DEFAULT_HPARAMS["displacement"])
-    sd = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
-    opt = torch.optim.Adam(list(sd.values()), DEFAULT_HPARAMS["learning_rate"])
+    if device == "cpu":
+        torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(1234)
-    imgs = torch.rand(batch_size, 6, height, width, generator=g) * 2 - 1
-    flow = torch.randn(batch_size, 2, height, width, generator=g) * 5
-    occ = (torch.rand(batch_size, 1, height, width, generator=g) < 0.3).float()
+    imgs = (torch.rand(batch_size, 6, height, width, generator=g) * 2 - 1).to(device)
+    flow = (torch.randn(batch_size, 2, height, width, generator=g) * 5).to(device)
+    occ = (torch.rand(batch_size, 1, height, width, generator=g) < 0.3).float().to(device)
+    from oracle import ref_loader
 
-    def run():
+    if ref_loader.available():
+        R = ref_loader.load()
+        torch.manual_seed(0)
+        model = R.model.FlowStageModel(dict(REF_HPARAMS)).to(device)
+        opt = model.configure_optimizers()
+
+        def run():
+            opt.zero_grad()
+            out = model.general_step_occ_aware((imgs, flow, occ), 0, "train")
+            loss = model.photo_weight * out[0] + model.smooth1_weight * out[1] + model.smooth2_weight * out[2]
+            loss.backward()
+            opt.step()
+            return loss.detach()
+
+        return run, torch.get_num_threads(), "reference"
+
+    from oracle import ocflow_oracle as O
+    from ocflow_b200.flow_net_cv import FlowNetCV   # only for parameter shapes / the reference's default init
+
+    torch.manual_seed(0)
+    net = FlowNetCV(REF_HPARAMS["displacement"])
+    sd = {k: v.detach().clone().to(device).requires_grad_(True) for k, v in net.state_dict().items()}
+    opt = torch.optim.Adam(list(sd.values()), REF_HPARAMS["learning_rate"])
+
+    def run_port():
         opt.zero_grad(set_to_none=True)
-        losses = O.occ_aware_step(sd, (imgs, flow, occ), DEFAULT_HPARAMS["displacement"])
-        loss = O.total_loss(losses, DEFAULT_HPARAMS["photo_weight"], DEFAULT_HPARAMS["smooth1_weight"], DEFAULT_HPARAMS["smooth2_weight"])
+        losses = O.occ_aware_step(sd, (imgs, flow, occ), REF_HPARAMS["displacement"])
+        loss = O.total_loss(losses, REF_HPARAMS["photo_weight"], REF_HPARAMS["smooth1_weight"], REF_HPARAMS["smooth2_weight"])
         loss.backward()
         opt.step()
-        return float(loss)
+        return loss.detach()
 
-    return run, torch.get_num_threads()
+    return run_port, torch.get_num_threads(), "port"
 
 
 def run_reference_arm(args):
+    """`--impl reference`: same config (batch, shape, warm-up, steps) as our arm, on the box's host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # other ranks exit 0 without work
-    b = args.cpu_sample_batch if (args.steps + args.warmup) <= 30 else 1
-    run, cores = cpu_step_runner(b, args.height, args.width)
-    for _ in range(min(args.warmup, 2)):
+    run, cores, kind = reference_step_runner(args.batch, args.height, args.width)
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         run()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        run()
+        loss = run()
     dt = time.perf_counter() - t0
-    value = b * args.steps / dt
-    sample = "%d steps x %d of %d pairs at %dx%d (oracle port of models/model.py:366-436, torch CPU fp32, %d threads)" % (
-        args.steps, b, args.batch, args.height, args.width, cores)
+    value = args.batch * args.steps / dt
+    what = ("the unmodified reference (baseline/_ref: models/model.py FlowStageModel.general_step_occ_aware + backward + Adam)"
+            if kind == "reference" else "oracle port of models/model.py:366-436 (no reference tree installed)")
+    sample = "%d steps x %d pairs at %dx%d after %d warm-up steps, %s, torch CPU fp32, %d threads" % (
+        args.steps, args.batch, args.height, args.width, warm, what, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload(args.height, args.width, args.batch), "cpu_sample_batch": b},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": workload(args.height, args.width, args.batch), "global_batch": args.batch, "parallelism": "cpu",
+                   "same_config_as_ours": True},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "final_loss": float(loss),
     }
     print(json.dumps(line), flush=True)
 
@@ -322,6 +353,51 @@ def live_kernel_times(step, batch, torch, height, reps=3):
     for name, ints, e0, e1 in rec:
         agg.setdefault(classify(name, ints), []).append(e0.elapsed_time(e1) * 1e3)
     return {k: (statistics.mean(v), len(v) / float(reps)) for k, v in agg.items()}
+
+
+def reference_gpu_legs(args, torch):
+    """Like-for-like GPU baseline: the UNMODIFIED reference step on the same B200 through torch's
+    generic CUDA kernels (eager -- its nonzero() host syncs rule out graph capture), under strict fp32 and torch's default
+    conv math, and the same reference code after ocflow_b200.patch.patch_reference() (the drop-in path).  pairs/s."""
+    from oracle import ref_loader
+
+    if not ref_loader.available():
+        return {"unavailable": "no reference tree installed (python -m oracle.install_ref)"}
+    import ocflow_b200.patch as P
+
+    out = {}
+
+    def timed(tag, tf32, patched):
+        torch.backends.cudnn.allow_tf32 = tf32
+        if patched:
+            P.patch_reference()
+        try:
+            run, _, _ = reference_step_runner(args.batch, args.height, args.width, device="cuda")
+            for _ in range(3):
+                run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 5
+            e0.record()
+            for _ in range(n):
+                loss = run()
+            e1.record()
+            torch.cuda.synchronize()
+            dt = e0.elapsed_time(e1) * 1e-3 / n
+            out[tag] = {"value": args.batch / dt, "unit": UNIT, "ms_per_step": 1e3 * dt, "loss": float(loss)}
+        finally:
+            if patched:
+                P.unpatch_reference()
+            torch.backends.cudnn.allow_tf32 = False
+            del run
+            torch.cuda.empty_cache()
+
+    timed("unpatched_fp32", False, False)
+    timed("unpatched_tf32_convs", True, False)
+    timed("patched_fp32", False, True)
+    out["what"] = ("baseline/_ref FlowStageModel('pwc', occ_aware).general_step_occ_aware + backward + Adam on cuda:0, eager, batch %d: "
+                   "as shipped (ATen kernels) vs after patch_reference() (our kernels behind the reference's own symbols)" % args.batch)
+    return out
 
 
 def ncu_traffic(kernel):
@@ -553,18 +629,23 @@ def main():
                                   "step0_loss_fp32": l32, "step0_loss_tf32": ltf, "step0_loss_rel_diff": abs(ltf - l32) / abs(l32)}
         del alt_step
 
-    # ---- CPU baseline (oracle port), bounded sample ----
+    # ---- the unmodified reference on this B200 (torch CUDA kernels) and the same code after patch_reference() ----
+    if world == 1 and not args.skip_refgpu:
+        try:
+            line["reference_on_gpu"] = reference_gpu_legs(args, torch)
+        except Exception as exc:   # informational leg: never lose the headline line over it
+            line["reference_on_gpu"] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+
+    # ---- CPU baseline: the reference's own step on the host cores, bounded sample (1 warm-up + 1 timed step at the full batch) ----
     if world == 1 and not args.skip_cpu:
-        b = args.cpu_sample_batch
-        run, cores = cpu_step_runner(b, H, W)
+        run, cores, kind = reference_step_runner(B, H, W)
         run()
         t0 = time.perf_counter()
-        nrep = 2
-        for _ in range(nrep):
-            run()
-        cdt = (time.perf_counter() - t0) / nrep
-        line["cpu_baseline"] = {"value": b / cdt, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "%d steps x %d of %d pairs at %dx%d after 1 warm-up (oracle port, torch CPU fp32)" % (nrep, b, B, H, W)}
+        run()
+        cdt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": B / cdt, "unit": UNIT, "cores": cores, "kind": kind,
+                                "sample": "1 step x %d pairs at %dx%d after 1 warm-up (%s, torch CPU fp32)" % (
+                                    B, H, W, "unmodified reference from baseline/_ref" if kind == "reference" else "oracle port")}
     print(json.dumps(line), flush=True)
     finish()
 
