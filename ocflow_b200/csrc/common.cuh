@@ -78,3 +78,35 @@ __device__ __forceinline__ float4 ocf_ldg_stream4(const float* p) {
                : "l"(p));
   return v;
 }
+
+// ---- quad gather / scatter helpers (warp.cu, loss.cu) ------------------------------------------------
+// 4 horizontally adjacent bilinear samples of a coherent flow touch 5 consecutive source pixels per tap row, i.e. two
+// 16-byte aligned groups q[0..7]; o = (first column) & 3 is lane dependent and is resolved with select chains.
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// v[j] = q[o + j], j = 0..4, o in 0..3
+__device__ __forceinline__ void funnel_gather(const float (&q)[8], int o, float (&v)[5]) {
+  float t[6];
+  const bool s2 = o & 2, s1 = o & 1;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) t[k] = s2 ? q[k + 2] : q[k];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) v[j] = s1 ? t[j + 1] : t[j];
+}
+
+// q[k] = v[k - o] (0 outside 0..4), k = 0..7
+__device__ __forceinline__ void funnel_scatter(const float (&v)[5], int o, float (&q)[8]) {
+  float t[6];
+  const bool s2 = o & 2, s1 = o & 1;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) t[k] = s1 ? (k >= 1 ? v[k - 1] : 0.f) : (k < 5 ? v[k] : 0.f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) q[k] = s2 ? (k >= 2 ? t[k - 2] : 0.f) : (k < 6 ? t[k] : 0.f);
+}
+
+__device__ __forceinline__ float4 ldg4_or_zero(const float* p, bool ok) {
+  return ok ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+

@@ -5,6 +5,8 @@
 // general_step_occ_aware (models/model.py:379-407).  Every kernel is a single streaming pass: per-thread
 // fp32 partials -> warp shuffle -> one double atomic per block, so the scalar losses are accumulated in
 // fp64 (the reference sums in fp32 with ATen's pairwise tree; both sit far inside the 1e-3 loss bar).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -344,6 +346,145 @@ occ_photo_fused_kernel(const float* __restrict__ img1, const float* __restrict__
   ocf_block_accumulate<6>(acc, sums);
 }
 
+// Quad version (W % 4 == 0, 16-byte aligned tensors): a thread owns 4 horizontally adjacent pixels.  When their 4 bilinear
+// samples are coherent (one tap-row pair, consecutive columns -- the normal case for a network flow) the 16 tap gathers
+// per channel become 4 x LDG.128 (two aligned groups per tap row) + a register funnel (common.cuh); otherwise the 16
+// scalar gathers are issued.  Compared with occ_photo_fused_kernel<4> this removes the 16 tap offsets + 16 validity flags
+// from the live state (126 -> about 64 registers, twice the resident warps) and 3/4 of the load instructions.
+template <int MINB>
+__global__ void __launch_bounds__(LT, MINB)
+occ_photo_quad_kernel(const float* __restrict__ img1, const float* __restrict__ img2, const float* __restrict__ flow,
+                      const float* __restrict__ range, const float* __restrict__ flow_gt, const float* __restrict__ occ_gt,
+                      double* __restrict__ sums, float* __restrict__ dflow, float* __restrict__ warped, int C, int H, int W,
+                      float a2) {
+  const int HW = H * W;
+  const int gpi = HW >> 2;  // quads per image
+  const int b = blockIdx.y;
+  float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float fw = (float)(W - 1), fh = (float)(H - 1);
+  const float dw = (float)max(W - 1, 1), dh = (float)max(H - 1, 1);
+  const float cx = (0.5f * fw) * (2.0f / dw), cy = (0.5f * fh) * (2.0f / dh);  // align_corners=True chain factor (== 1)
+  const float* fl_b = flow + (size_t)b * 2 * HW;
+  const float* i1_b = img1 + (size_t)b * C * HW;
+  const float* i2_b = img2 + (size_t)b * C * HW;
+  for (int gi = blockIdx.x * LT + threadIdx.x; gi < gpi; gi += gridDim.x * LT) {
+    const int q = gi << 2;
+    const int y = q / W, x = q - y * W;
+    const float4 U4 = __ldg(reinterpret_cast<const float4*>(fl_b + q)), V4 = __ldg(reinterpret_cast<const float4*>(fl_b + HW + q));
+    const float U[4] = {U4.x, U4.y, U4.z, U4.w}, V[4] = {V4.x, V4.y, V4.z, V4.w};
+    int x0[4], y0[4];
+    float wx1[4], wy1[4];   // east / south weights; west = (x0 + 1) - ix is recomputed as 1 - wx1 only where exact (see below)
+    float wx0[4], wy0[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      // align_corners=True coordinates, reference op order (models/model.py:211-212 + ATen unnormalize); x*0.5f == x/2 exactly
+      float ix = __fmul_rn(__fmul_rn(__fadd_rn(__fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn((float)(x + i), U[i])), dw), 1.0f), 1.0f), 0.5f), fw);
+      float iy = __fmul_rn(__fmul_rn(__fadd_rn(__fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn((float)y, V[i])), dh), 1.0f), 1.0f), 0.5f), fh);
+      if (!(ix > -2147483648.0f && ix < 2147483520.0f)) ix = -100.f;
+      if (!(iy > -2147483648.0f && iy < 2147483520.0f)) iy = -100.f;
+      const float fx0 = floorf(ix), fy0 = floorf(iy);
+      x0[i] = (int)fx0; y0[i] = (int)fy0;
+      wx1[i] = ix - fx0; wx0[i] = (fx0 + 1.f) - ix; wy1[i] = iy - fy0; wy0[i] = (fy0 + 1.f) - iy;
+    }
+    bool fast = x0[0] >= -8 && x0[0] <= W && y0[0] >= -2 && y0[0] <= H;
+#pragma unroll
+    for (int i = 1; i < 4; ++i) fast = fast && y0[i] == y0[0] && x0[i] == x0[0] + i;
+    float e[4] = {0.f, 0.f, 0.f, 0.f}, gx[4] = {0.f, 0.f, 0.f, 0.f}, gy[4] = {0.f, 0.f, 0.f, 0.f};
+    // aligned-group plan of the coherent case
+    const int a = x0[0] & ~3, o = x0[0] - a;
+    const bool vn = y0[0] >= 0 && y0[0] < H, vs = y0[0] + 1 >= 0 && y0[0] + 1 < H;
+    const bool va = a >= 0 && a + 3 < W, vb = a + 4 >= 0 && a + 7 < W;
+    const int rowN = y0[0] * W + a;
+#pragma unroll 1
+    for (int c = 0; c < C; ++c) {
+      const float* ip = i2_b + c * HW;
+      const float4 t4 = __ldg(reinterpret_cast<const float4*>(i1_b + c * HW + q));
+      const float t1[4] = {t4.x, t4.y, t4.z, t4.w};
+      float ta[4], tb[4], tc[4], td[4];
+      if (fast) {
+        const float4 a0 = ldg4_or_zero(ip + rowN, vn && va), a1 = ldg4_or_zero(ip + rowN + 4, vn && vb);
+        const float4 b0 = ldg4_or_zero(ip + rowN + W, vs && va), b1 = ldg4_or_zero(ip + rowN + W + 4, vs && vb);
+        const float qn[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float qs[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float n5[5], s5[5];
+        funnel_gather(qn, o, n5);
+        funnel_gather(qs, o, s5);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { ta[i] = n5[i]; tb[i] = n5[i + 1]; tc[i] = s5[i]; td[i] = s5[i + 1]; }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const bool vx0 = x0[i] >= 0 && x0[i] < W, vx1 = x0[i] + 1 >= 0 && x0[i] + 1 < W;
+          const bool vy0 = y0[i] >= 0 && y0[i] < H, vy1 = y0[i] + 1 >= 0 && y0[i] + 1 < H;
+          const int off = y0[i] * W + x0[i];
+          ta[i] = (vx0 && vy0) ? __ldg(ip + off) : 0.f; tb[i] = (vx1 && vy0) ? __ldg(ip + off + 1) : 0.f;
+          tc[i] = (vx0 && vy1) ? __ldg(ip + off + W) : 0.f; td[i] = (vx1 && vy1) ? __ldg(ip + off + W + 1) : 0.f;
+        }
+      }
+      float wv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float sacc = 0.f;
+        sacc = fmaf(ta[i], wx0[i] * wy0[i], sacc); sacc = fmaf(tb[i], wx1[i] * wy0[i], sacc);
+        sacc = fmaf(tc[i], wx0[i] * wy1[i], sacc); sacc = fmaf(td[i], wx1[i] * wy1[i], sacc);
+        wv[i] = sacc;
+        const float d = sacc - t1[i];
+        const float r2 = fmaf(d, d, a2);
+        const float inv = rsqrtf(r2);     // rho = r2 * inv, rho' = d * inv   (MUFU.RSQ, <= 2 ulp: far inside the loss tolerance)
+        e[i] = fmaf(r2, inv, e[i]);
+        const float gr = d * inv;
+        gx[i] = fmaf(gr, (tb[i] - ta[i]) * wy0[i] + (td[i] - tc[i]) * wy1[i], gx[i]);
+        gy[i] = fmaf(gr, (tc[i] - ta[i]) * wx0[i] + (td[i] - tb[i]) * wx1[i], gy[i]);
+      }
+      if (warped != nullptr) *reinterpret_cast<float4*>(warped + ((size_t)b * C + c) * HW + q) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+    }
+    float occv[4], vis[4];
+    if (range != nullptr) {
+      const float4 r4 = __ldg(reinterpret_cast<const float4*>(range + (size_t)b * HW + q));
+      const float r[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) occv[i] = 1.0f - fminf(fmaxf(r[i], 0.f), 1.f);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) occv[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) vis[i] = 1.0f - occv[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc[0] += e[i] * vis[i]; acc[1] += vis[i]; acc[2] += e[i] * occv[i]; acc[3] += occv[i];
+    }
+    if (dflow != nullptr) {
+      float* df = dflow + (size_t)b * 2 * HW + q;
+      *reinterpret_cast<float4*>(df) = make_float4(gx[0] * vis[0] * cx, gx[1] * vis[1] * cx, gx[2] * vis[2] * cx, gx[3] * vis[3] * cx);
+      *reinterpret_cast<float4*>(df + HW) = make_float4(gy[0] * vis[0] * cy, gy[1] * vis[1] * cy, gy[2] * vis[2] * cy, gy[3] * vis[3] * cy);
+    }
+    if (flow_gt != nullptr) {
+      const float4 gu = __ldg(reinterpret_cast<const float4*>(flow_gt + (size_t)b * 2 * HW + q));
+      const float4 gv = __ldg(reinterpret_cast<const float4*>(flow_gt + (size_t)b * 2 * HW + HW + q));
+      const float gus[4] = {gu.x, gu.y, gu.z, gu.w}, gvs[4] = {gv.x, gv.y, gv.z, gv.w};
+      const float4 Ur = __ldg(reinterpret_cast<const float4*>(fl_b + q)), Vr = __ldg(reinterpret_cast<const float4*>(fl_b + HW + q));  // L1 hit
+      const float Uq[4] = {Ur.x, Ur.y, Ur.z, Ur.w}, Vq[4] = {Vr.x, Vr.y, Vr.z, Vr.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float du = Uq[i] - gus[i], dv = Vq[i] - gvs[i];
+        acc[4] += du * du + dv * dv;
+      }
+    }
+    if (occ_gt != nullptr) {
+      // F.binary_cross_entropy(input=occ_gt, target=occ_pred)  -- swapped on purpose, models/model.py:407
+      const float4 p4 = __ldg(reinterpret_cast<const float4*>(occ_gt + (size_t)b * HW + q));
+      const float pin[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float lp = fmaxf(logf(pin[i]), -100.f), l1p = fmaxf(logf(1.0f - pin[i]), -100.f);
+        acc[5] += -(occv[i] * lp + (1.0f - occv[i]) * l1p);
+      }
+    }
+  }
+  ocf_block_accumulate<6>(acc, sums);
+}
+
 // ---- supervised pair losses ---------------------------------------------------------------------
 __global__ void __launch_bounds__(LT)
 pair_loss_kernel(const float* __restrict__ a, const float* __restrict__ b, double* __restrict__ sum, float* __restrict__ grad,
@@ -485,7 +626,17 @@ extern "C" int ocf_occ_photo_fused(const float* img1, const float* img2, const f
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   dim3 grid(bx, B);
-  if (vec)
+  if (vec && OCF_OPF_VPX == 4) {
+    // one quad per thread (no grid-stride repetition needed up to the cap): enough CTAs for >= 6 per SM
+    int qx = (gpi + LT - 1) / LT;
+    const int qcap = (8 * OCF_SM_COUNT + B - 1) / B;
+    if (qx > qcap) qx = qcap;
+    static const int minb = []() { const char* e = getenv("OCF_OPF_MINB"); return e ? atoi(e) : 2; }();   // developer knob (tuning runs)
+    if (minb == 3)
+      occ_photo_quad_kernel<3><<<dim3(qx, B), LT, 0, s>>>(img1, img2, flow, range_map, flow_gt, occ_gt, sums, dflow_unit, warped_out, C, H, W, alpha * alpha);
+    else
+      occ_photo_quad_kernel<2><<<dim3(qx, B), LT, 0, s>>>(img1, img2, flow, range_map, flow_gt, occ_gt, sums, dflow_unit, warped_out, C, H, W, alpha * alpha);
+  } else if (vec)
     occ_photo_fused_kernel<OCF_OPF_VPX><<<grid, LT, 0, s>>>(img1, img2, flow, range_map, flow_gt, occ_gt, sums, dflow_unit, warped_out, C, H, W, alpha * alpha);
   else
     occ_photo_fused_kernel<1><<<grid, LT, 0, s>>>(img1, img2, flow, range_map, flow_gt, occ_gt, sums, dflow_unit, warped_out, C, H, W, alpha * alpha);

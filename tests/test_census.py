@@ -45,18 +45,21 @@ def test_oracle_census_gradcheck_fp64():
 def test_cuda_census_matches_oracle(shape, m, use_occ):
     import ocflow_b200 as ocf
 
-    for noise in (0.05, 0.002):   # far from / close to the steep part of the soft sign
+    # The oracle runs in fp64.  Close to the steep part of the soft sign (noise 0.002) the term is ill-conditioned in fp32:
+    # the fp32 ORACLE's own gradient is 1.2e-4 (rel. max) away from its fp64 run on these inputs, so the fp32 kernel is held
+    # to 5e-4 there and to 1e-4 on the well-conditioned case.
+    for noise, gtol in ((0.05, 1e-4), (0.002, 5e-4)):
         pred, img, occ = _inputs(*shape, seed=7, noise=noise)
         occ = occ if use_occ else None
-        p_ref = pred.clone().requires_grad_(True)
-        ref = O.census_loss(p_ref, img, occ, m)
+        p_ref = pred.double().requires_grad_(True)
+        ref = O.census_loss(p_ref, img.double(), None if occ is None else occ.double(), m)
         ref.backward()
         p = pred.cuda().requires_grad_(True)
         mine = ocf.census_loss(p, img.cuda(), None if occ is None else occ.cuda(), m)
         assert_scalar_close(mine, ref, 1e-3 if float(ref) > 0 else 1e-9, "census loss")
         mine.backward()
         if float(p_ref.grad.abs().max()) > 0:
-            assert_close(p.grad, p_ref.grad, 1e-4, "d census / d pred")
+            assert_close(p.grad, p_ref.grad, gtol, "d census / d pred")
         else:
             assert float(p.grad.abs().max()) == 0.0
 
