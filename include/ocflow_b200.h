@@ -33,7 +33,7 @@ typedef void* ocf_stream_t; /* cudaStream_t */
 #define OCF_EUNSUPPORTED (-3) /* argument value outside what the kernels implement */
 #define OCF_EALIGN (-4)       /* pointer not aligned to 4 bytes / stride not usable */
 
-#define OCF_ABI_VERSION 2
+#define OCF_ABI_VERSION 3
 #define OCF_MAX_DISPLACEMENT 16
 
 int ocf_abi_version(void);
@@ -77,6 +77,23 @@ int ocf_corr_bwd(const float* grad_out, const float* out_act, const float* f1, c
                  long long act_bstride, float leaky_slope, const unsigned char* mask, ocf_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused pyramid level (FlowNetCV, cost_volume_flow_net.py:186-190 and the 4 other levels):
+ *   corr = LeakyReLU(compute_cost_volume(c1n, c2n, 4)), c1n = (f1 - mean) * inv_std, c2n likewise, with
+ *   norm = {mean, inv_std} (device, from ocf_normalize_stats) applied ON LOAD; zero padding stays zero after the
+ *   normalisation exactly as in normalize_features -> F.pad.  d = 4 only; runs on the tensor cores (tcgen05, 3xTF32).
+ *   out / f1n_out may point into a wider concat buffer (batch strides in elements, 0 = dense); f2n_out (dense, may be
+ *   NULL) receives the normalised second feature map for the backward; mask_out as in ocf_corr_fwd.
+ *   norm == NULL: plain correlation (f1n_out / f2n_out must then be NULL).
+ * ocf_level_corr_bwd: ocf_corr_bwd(d = 4, sign bitmask) with f1n read in place (batch stride f1n_bstride).
+ * ------------------------------------------------------------------------------------------- */
+int ocf_level_corr_fwd(const float* f1, const float* f2, const float* norm, float* out, long long out_bstride,
+                       float* f1n_out, long long f1n_bstride, float* f2n_out, unsigned char* mask_out, int B, int C,
+                       int H, int W, float leaky_slope, ocf_stream_t stream);
+int ocf_level_corr_bwd(const float* grad_out, long long g_bstride, const unsigned char* mask, const float* f1n,
+                       long long f1n_bstride, const float* f2n, float* df1, float* df2, int B, int C, int H, int W,
+                       float leaky_slope, ocf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Feature normalisation.  Replaces normalize_features(feature_list, normalize, center,
  *   moments_across_channels, moments_across_images)  models/networks/correlation_layer.py:42-82.
  *   All T tensors of the list must share one shape [B,C,H,W] (they do at every call site).
@@ -90,6 +107,10 @@ int ocf_corr_bwd(const float* grad_out, const float* out_act, const float* f1, c
 #define OCF_NORM_ACROSS_IMAGES 8
 int ocf_normalize_fwd(const float* const* xs, float* const* ys, int T, int B, int C, int H, int W,
                       int flags, float* stats, ocf_stream_t stream);
+/* statistics pass of ocf_normalize_fwd alone (fills `stats`; the {mean, inv_std} applied to group g are
+ * stats[6*NG + 2*g], stats[6*NG + 2*g + 1], NG = T*B*G).  With moments_across_images (the FlowNetCV call sites,
+ * cost_volume_flow_net.py:171,187,...) every group carries the same scalar pair. */
+int ocf_normalize_stats(const float* const* xs, int T, int B, int C, int H, int W, int flags, float* stats, ocf_stream_t stream);
 /* grads wrt every input, differentiating through the statistics (no detach in the reference).
  * red workspace (8-byte aligned): 8*T*B*G floats. */
 int ocf_normalize_bwd(const float* const* grad_ys, const float* const* xs, float* const* grad_xs,

@@ -32,6 +32,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "corr_tc.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -655,7 +656,7 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
                const float* __restrict__ oact, const unsigned char* __restrict__ mask, const float* __restrict__ f1,
                const float* __restrict__ f2, float* __restrict__ df1,
                float* __restrict__ df2, int C, int H, int W, long long g_bstride, long long a_bstride, float inv_c, float slope,
-               int nmodes, int first_mode, int ksplit) {
+               int nmodes, int first_mode, int ksplit, long long f1_bstride, long long f2_bstride) {
   constexpr int D = T::D, PX = T::PX, ND = T::ND, TH = T::TH, TW = T::TW, CC = T::CC, STAGES = T::STAGES;
   constexpr int S1 = T::S1, S2 = T::S2, F2H = T::F2H, F2W = T::F2W, WIN = T::WIN;
   constexpr bool TMA = STG == STG_TMA;
@@ -807,7 +808,8 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
           if (!((mbits[dx / 3] >> ((dx % 3) * PX + p)) & 1u)) G[dx][p] *= slope;
     }
   }
-  const float* fo = (mode == 0 ? f2 : f1) + (size_t)b * C * H * W;
+  const float* fo = (mode == 0 ? f2 + (size_t)b * (f2_bstride ? (size_t)f2_bstride : (size_t)C * H * W)
+                               : f1 + (size_t)b * (f1_bstride ? (size_t)f1_bstride : (size_t)C * H * W));
   auto issue = [&](int i) {
     stage_box_async<CC, F2H, F2W, S2, T::THREADS, STG == STG_ASYNC16>(smem + (i % STAGES) * T::F2_STAGE, fo, (cr.begin + i) * CC, C, H, W,
                                                                       y0 - D, x0 - D);
@@ -1057,9 +1059,12 @@ extern "C" int ocf_corr_fwd(const float* f1, const float* f2, float* out, int B,
   const long long nd = 2 * d + 1;
   OCF_REQUIRE(out_bstride == 0 || out_bstride >= nd * nd * H * W, OCF_ESHAPE);
   OCF_REQUIRE(B <= 8191, OCF_EUNSUPPORTED);
-  OCF_REQUIRE(mask_out == nullptr || (d == 4 && norm == nullptr), OCF_EUNSUPPORTED);  // only the tiled kernels emit the sign mask
+  OCF_REQUIRE(mask_out == nullptr || d == 4, OCF_EUNSUPPORTED);  // only the d = 4 kernels emit the sign mask
   cudaStream_t s = ocf_cast_stream(stream);
   const float inv_c = 1.0f / (float)C;
+  // d = 4: tensor-core kernel (tcgen05, 3xTF32) unless the developer knob OCF_CORR_TC=0 selects the fp32 FMA kernels
+  static const int use_tc = []() { const char* e = getenv("OCF_CORR_TC"); return e ? atoi(e) : 1; }();
+  if (d == 4 && use_tc) return ocf_corr_fwd_tc_launch(f1, f2, out, mask_out, norm, nullptr, 0, nullptr, B, C, H, W, out_bstride, leaky_slope, s);
   if (d == 4 && norm == nullptr) {
     using T = Tile4;
     const size_t smem = sizeof(float) * T::STAGES * (T::F1_STAGE + T::F2_STAGE);
@@ -1096,9 +1101,11 @@ extern "C" int ocf_corr_fwd(const float* f1, const float* f2, float* out, int B,
   return ocf_launch_status();
 }
 
-extern "C" int ocf_corr_bwd(const float* grad_out, const float* out_act, const float* f1, const float* f2, float* df1,
-                            float* df2, int B, int C, int H, int W, int d, long long g_bstride, long long act_bstride,
-                            float leaky_slope, const unsigned char* mask, ocf_stream_t stream) {
+// f1_bstride / f2_bstride: batch strides of the feature operands in elements (0 = dense): the fused level op keeps the
+// normalised first feature map inside the decoder's concat buffer (level.cu)
+int ocf_corr_bwd_impl(const float* grad_out, const float* out_act, const float* f1, const float* f2, float* df1,
+                      float* df2, int B, int C, int H, int W, int d, long long g_bstride, long long act_bstride,
+                      float leaky_slope, const unsigned char* mask, long long f1_bstride, long long f2_bstride, ocf_stream_t stream) {
   OCF_REQUIRE_PTR(grad_out); OCF_REQUIRE_PTR(f1); OCF_REQUIRE_PTR(f2);
   OCF_REQUIRE(df1 != nullptr || df2 != nullptr, OCF_ENULL);
   OCF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, OCF_ESHAPE);
@@ -1119,7 +1126,7 @@ extern "C" int ocf_corr_bwd(const float* grad_out, const float* out_act, const f
     const int gx = (W + T::TW - 1) / T::TW, gy = (H + T::TH - 1) / T::TH;
     const int ks = pick_ksplit((long long)gx * gy * B * nmodes, C, 2 * T::CC, false, out_act != nullptr ? 30.0 : (mask != nullptr ? 18.0 : 16.0));
     dim3 grid(gx, gy, B * nmodes * ks);
-    const bool vec = (W % 4 == 0) && ocf_aligned16(f1) && ocf_aligned16(f2) && (df1 == nullptr || ocf_aligned16(df1)) &&
+    const bool vec = (W % 4 == 0) && (f1_bstride % 4 == 0) && (f2_bstride % 4 == 0) && ocf_aligned16(f1) && ocf_aligned16(f2) && (df1 == nullptr || ocf_aligned16(df1)) &&
                      (df2 == nullptr || ocf_aligned16(df2));
     CUtensorMap m1, m2, mg;
     memset(&m1, 0, sizeof(m1));
@@ -1128,7 +1135,8 @@ extern "C" int ocf_corr_bwd(const float* grad_out, const float* out_act, const f
     const long long gbs = g_bstride ? g_bstride : nd * nd * H * W;
     const long long abs_ = act_bstride ? act_bstride : nd * nd * H * W;
     bool tma = vec && ocf_aligned16(grad_out) && (out_act == nullptr || ocf_aligned16(out_act)) && (gbs % 4 == 0) && (abs_ % 4 == 0);
-    tma = tma && make_map(&m1, f1, B, C, H, W, T::S2, T::F2H, T::CC) && make_map(&m2, f2, B, C, H, W, T::S2, T::F2H, T::CC) &&
+    tma = tma && (f1_bstride % 4 == 0) && (f2_bstride % 4 == 0);
+    tma = tma && make_map(&m1, f1, B, C, H, W, T::S2, T::F2H, T::CC, f1_bstride) && make_map(&m2, f2, B, C, H, W, T::S2, T::F2H, T::CC, f2_bstride) &&
           make_map(&mg, grad_out, B, (int)(nd * nd), H, W, T::S2, T::TH, T::ND, gbs);
     if (tma) {
       const size_t gstage = sizeof(float) * T::ND * T::ND * T::TH * T::S2;  // coefficient staging, reused by ring + red
@@ -1136,16 +1144,23 @@ extern "C" int ocf_corr_bwd(const float* grad_out, const float* out_act, const f
       auto kernel = corr_bwd_tiled<T, BWD_CR, STG_TMA>;
       if (int e = set_smem(kernel, smem)) return e;
       if (int e = launch_kernel(kernel, grid, T::THREADS + 32, smem, s, 1, m1, m2, mg, grad_out, out_act, mask, f1, f2, df1, df2, C, H, W, g_bstride,
-                                act_bstride, inv_c, leaky_slope, nmodes, first, ks)) return e;
+                                act_bstride, inv_c, leaky_slope, nmodes, first, ks, f1_bstride, f2_bstride)) return e;
     } else {
       auto kernel = vec ? corr_bwd_tiled<T, BWD_CR, STG_ASYNC16> : corr_bwd_tiled<T, BWD_CR, STG_ASYNC4>;
       if (int e = set_smem(kernel, smem)) return e;
       if (int e = launch_kernel(kernel, grid, T::THREADS, smem, s, 1, m1, m2, mg, grad_out, out_act, mask, f1, f2, df1, df2, C, H, W, g_bstride,
-                                act_bstride, inv_c, leaky_slope, nmodes, first, ks)) return e;
+                                act_bstride, inv_c, leaky_slope, nmodes, first, ks, f1_bstride, f2_bstride)) return e;
     }
   } else {
+    OCF_REQUIRE(f1_bstride == 0 && f2_bstride == 0, OCF_EUNSUPPORTED);
     dim3 grid((H * W + 127) / 128, C, B);
     corr_bwd_generic<<<grid, 128, 0, s>>>(grad_out, out_act, f1, f2, df1, df2, C, H, W, d, g_bstride, act_bstride, inv_c, leaky_slope);
   }
   return ocf_launch_status();
+}
+
+extern "C" int ocf_corr_bwd(const float* grad_out, const float* out_act, const float* f1, const float* f2, float* df1,
+                            float* df2, int B, int C, int H, int W, int d, long long g_bstride, long long act_bstride,
+                            float leaky_slope, const unsigned char* mask, ocf_stream_t stream) {
+  return ocf_corr_bwd_impl(grad_out, out_act, f1, f2, df1, df2, B, C, H, W, d, g_bstride, act_bstride, leaky_slope, mask, 0, 0, stream);
 }

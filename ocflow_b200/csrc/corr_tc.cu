@@ -1,0 +1,356 @@
+// Local cost volume (d = 4, 81 displacements) on the 5th-generation tensor cores: tcgen05.mma kind::tf32 with the
+// accumulator in tensor memory, fp32 parity kept by the 3xTF32 operand split.
+//
+//   out[b, k(dy,dx), y, x] = 1/C * sum_c f1[b,c,y,x] * f2[b,c,y+dy,x+dx]        (correlation_layer.py:7-40)
+//
+// GEMM view of one CTA tile: M = 128 pixels (16 rows x 8 columns), N = 384 halo pixels (24 x 16), K = channels.
+// D = F1^T F2 contains, for every pixel, the products with ALL 384 halo pixels; the 81 wanted ones form a band that the
+// epilogue cuts out.  The band wastes 384/81 = 4.7x of the tensor-core work and the operand split another 3x, which is
+// still 2-3x faster than the fp32 FMA pipe (the FMA kernels in corr.cu are bound by shared-memory bandwidth at ~40 %
+// of the FMA peak).
+//
+// 3xTF32: x = hi + lo with hi = tf32(x) (round to nearest, low 13 mantissa bits zero) and lo = tf32(x - hi);
+// a.b ~= a_hi.b_hi + a_hi.b_lo + a_lo.b_hi, fp32 accumulation in TMEM.  Dropped terms are ~2^-22 |a||b| per product
+// (measured against the fp64 oracle: 1e-6 relative, the FMA kernel has 1e-7; the bar is 1e-4).
+//
+// Roles in the 288-thread CTA (one CTA per SM, persistent over tiles):
+//   warps 4-7  producers   global (LDG.128, zero fill outside the image / past the last channel) -> split -> shared memory
+//                          in the UMMA MN-major no-swizzle canonical layout (16-byte chunks of 4 pixels, K stride 16 B, chunk
+//                          stride 128 B); optional feature normalisation (x - mean) * inv_std folded in (normalize_features,
+//                          correlation_layer.py:42-82: zero padding stays zero AFTER normalisation, as in the reference)
+//   warp 8     MMA issuer  one thread: 6 x tcgen05.mma (M128 N192 K8) per 8-channel stage, tcgen05.commit -> mbarriers
+//   warps 0-3  epilogue    tcgen05.ld (TMEM lane = pixel) -> band selection by ADDRESS (the register index of a column is
+//                          static, the output plane it belongs to is lane dependent) -> staging tile in shared memory ->
+//                          1/C, LeakyReLU, sign bitmask, 128-bit coalesced stores
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "corr_tc.cuh"
+
+namespace {
+
+constexpr int D = 4, ND = 9, NP = 81;
+constexpr int TH = 16, TW = 8;             // pixel tile (M = 128, m = y * 8 + x)
+constexpr int HROWS = TH + 2 * D;          // 24 halo rows
+constexpr int NHALF = HROWS * 8;           // 192 accumulator columns per x-half of the halo (n = half * 192 + row * 8 + x % 8)
+constexpr int KC = 8;                      // channels per stage = K of one kind::tf32 MMA
+constexpr int STAGES = 4;
+constexpr int A_BYTES = TH * TW * KC * 4;  // 4096
+constexpr int B_BYTES = 2 * NHALF * KC * 4;  // 12288
+constexpr int OFF_ALO = A_BYTES, OFF_BHI = 2 * A_BYTES, OFF_BLO = 2 * A_BYTES + B_BYTES;
+constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);  // 32768
+constexpr int PS = 132;                    // floats per staged output plane (128 pixels + 4: 16-byte aligned rows, <= 2-way bank conflicts)
+constexpr int STAGING_BYTES = NP * PS * 4;
+constexpr int THREADS = 288;
+constexpr int TMEM_COLS = 512;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = smem_u32(bar);
+  unsigned ok;
+#ifdef OCF_TC_WATCHDOG
+  unsigned spins = 0;
+#endif
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+#ifdef OCF_TC_WATCHDOG
+    if (!ok && ++spins > (1u << 22)) __trap();   // developer builds: turn a protocol bug into an error instead of a hang
+#endif
+  } while (!ok);
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// shared-memory matrix descriptor, no swizzle: start address, leading (K-group) byte offset, stride (16-byte chunk) byte offset
+__device__ __forceinline__ unsigned long long umma_desc(unsigned addr, unsigned lbo_bytes, unsigned sbo_bytes) {
+  return (unsigned long long)((addr >> 4) & 0x3FFF) | ((unsigned long long)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((unsigned long long)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_tf32(unsigned d_tmem, unsigned long long da, unsigned long long db, unsigned idesc, unsigned acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void sts128(unsigned addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+struct TileCoord {
+  int b, y0, x0;
+};
+__device__ __forceinline__ TileCoord tile_coord(int tile, int tiles_x, int tiles_y) {
+  TileCoord t;
+  const int txi = tile % tiles_x, r = tile / tiles_x;
+  t.x0 = txi * TW;
+  t.y0 = (r % tiles_y) * TH;
+  t.b = r / tiles_y;
+  return t;
+}
+
+// VEC: rows are 16-byte aligned (W % 4 == 0, aligned base pointers) -> one LDG.128 per 4-pixel chunk and 128-bit output stores;
+// otherwise (KITTI / Sintel pyramid widths) per-element predicated loads and stores: no re-pitching copy is needed.
+template <bool VEC>
+__global__ void __launch_bounds__(THREADS, 1)
+corr_fwd_tc_kernel(const float* __restrict__ f1, const float* __restrict__ f2, float* __restrict__ out, unsigned char* __restrict__ mask,
+                   const float* __restrict__ norm, float* __restrict__ f1n_out, long long f1n_bstride, float* __restrict__ f2n_out, int C, int H,
+                   int W, long long out_bstride, float inv_c, float slope, int tiles_x, int tiles_y, int ntiles) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES], tmem_full_bar, tmem_empty_bar[2];
+  __shared__ unsigned tmem_base_slot;
+  float* staging = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nst = (C + KC - 1) / KC;
+  const size_t HW = (size_t)H * W;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    mbar_init(&tmem_empty_bar[0], 128);
+    mbar_init(&tmem_empty_bar[1], 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tb = tmem_base_slot;
+
+  if (warp >= 4 && warp < 8) {
+    // =========================== producers ===========================
+    const int p = tid - 128;
+    const int k = p & 7;                         // channel within the stage
+    const int ja = (p >> 3) & 1, rowa = p >> 4;  // A unit i (0,1): pixel row rowa + 8 i, 4-pixel chunk ja
+    const int jb = (p >> 3) & 3, rowb = p >> 5;  // B unit i (0..5): halo row rowb + 4 i, chunk jb (x-half jb >> 1)
+    const unsigned offa = (unsigned)((rowa * 2 + ja) * 128 + k * 16);
+    const unsigned offb = (unsigned)(((jb >> 1) * (NHALF / 4) + rowb * 2 + (jb & 1)) * 128 + k * 16);
+    float nmean = 0.f, ninv = 1.f;
+    if (norm != nullptr) { nmean = __ldg(norm); ninv = __ldg(norm + 1); }
+    int n = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const TileCoord tc = tile_coord(tile, tiles_x, tiles_y);
+      const float* f1b = f1 + (size_t)tc.b * C * HW;
+      const float* f2b = f2 + (size_t)tc.b * C * HW;
+      const int xa = tc.x0 + 4 * ja, xb = tc.x0 - D + 4 * jb;
+      for (int s = 0; s < nst; ++s, ++n) {
+        const int slot = n % STAGES;
+        if (n >= STAGES) mbar_wait(&empty_bar[slot], ((n / STAGES) - 1) & 1);
+        const int c = s * KC + k;
+        const bool cok = c < C;
+        float4 v[8];
+        unsigned okm[8];   // per-element validity (bit e) of the 8 units
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const bool isa = i < 2;
+          const int y = isa ? tc.y0 + rowa + 8 * i : tc.y0 - D + rowb + 4 * (i - 2);
+          const int x = isa ? xa : xb;
+          const float* src = (isa ? f1b : f2b) + ((size_t)c * H + y) * W + x;
+          const bool rok = cok && y >= 0 && y < H;
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (VEC) {
+            const bool ok = rok && x >= 0 && x < W;
+            okm[i] = ok ? 0xFu : 0u;
+            if (ok) v[i] = __ldg(reinterpret_cast<const float4*>(src));
+          } else {
+            unsigned m = 0u;
+            if (rok) {
+              if (x >= 0 && x < W) { v[i].x = __ldg(src); m |= 1u; }
+              if (x + 1 >= 0 && x + 1 < W) { v[i].y = __ldg(src + 1); m |= 2u; }
+              if (x + 2 >= 0 && x + 2 < W) { v[i].z = __ldg(src + 2); m |= 4u; }
+              if (x + 3 >= 0 && x + 3 < W) { v[i].w = __ldg(src + 3); m |= 8u; }
+            }
+            okm[i] = m;
+          }
+        }
+        const unsigned sbase = smem_u32(smem) + (unsigned)slot * STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const bool isa = i < 2;
+          float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+          if (norm != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) e[q] = (okm[i] >> q) & 1u ? (e[q] - nmean) * ninv : 0.f;
+            if (isa && f1n_out != nullptr && okm[i]) {
+              // the normalised first feature map is an output of the level (it is concatenated into the decoder input,
+              // cost_volume_flow_net.py:190): every A element is loaded exactly once per launch, so it is written from here
+              const int y = tc.y0 + rowa + 8 * i;
+              float* dst = f1n_out + (size_t)tc.b * (f1n_bstride ? (size_t)f1n_bstride : (size_t)C * HW) + ((size_t)c * H + y) * W + xa;
+              if (VEC) *reinterpret_cast<float4*>(dst) = make_float4(e[0], e[1], e[2], e[3]);
+              else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if ((okm[i] >> q) & 1u) dst[q] = e[q];
+              }
+            }
+            if (!isa && f2n_out != nullptr && okm[i] && (jb == 1 || jb == 2)) {
+              // the normalised second feature map (needed by the backward): the interior of the halo box -- rows 4..19, chunks
+              // 1 and 2 -- is this tile's own 16 x 8 pixels, loaded by exactly one tile
+              const int r = rowb + 4 * (i - 2);
+              if (r >= D && r < D + TH) {
+                float* dst = f2n_out + (size_t)tc.b * C * HW + ((size_t)c * H + (tc.y0 - D + r)) * W + xb;
+                if (VEC) *reinterpret_cast<float4*>(dst) = make_float4(e[0], e[1], e[2], e[3]);
+                else {
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) if ((okm[i] >> q) & 1u) dst[q] = e[q];
+                }
+              }
+            }
+          }
+          float hi[4], lo[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { hi[q] = tf32_rna(e[q]); lo[q] = tf32_rna(e[q] - hi[q]); }
+          const unsigned a = sbase + (isa ? offa + (unsigned)(i * 16 * 128) : OFF_BHI + offb + (unsigned)((i - 2) * 8 * 128));
+          sts128(a, hi[0], hi[1], hi[2], hi[3]);
+          sts128(a + (isa ? A_BYTES : B_BYTES), lo[0], lo[1], lo[2], lo[3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbar_arrive(&full_bar[slot]);
+      }
+    }
+  } else if (warp == 8) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      // instruction descriptor: D fp32, A/B tf32, both MN-major, N = 192, M = 128
+      constexpr unsigned IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(NHALF >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+      int n = 0, t = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+        for (int s = 0; s < nst; ++s, ++n) {
+          const int slot = n % STAGES;
+          mbar_wait(&full_bar[slot], (n / STAGES) & 1);
+          tc_fence_after();
+          const unsigned sbase = smem_u32(smem) + (unsigned)slot * STAGE_BYTES;
+          const unsigned long long ahi = umma_desc(sbase, STAGE_BYTES, 128), alo = umma_desc(sbase + OFF_ALO, STAGE_BYTES, 128);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (s == 0) {   // the epilogue must have drained this half of the previous tile's accumulator
+              mbar_wait(&tmem_empty_bar[h], (t & 1) ^ 1);
+              tc_fence_after();
+            }
+            const unsigned long long bhi = umma_desc(sbase + OFF_BHI + h * (B_BYTES / 2), STAGE_BYTES, 128);
+            const unsigned long long blo = umma_desc(sbase + OFF_BLO + h * (B_BYTES / 2), STAGE_BYTES, 128);
+            const unsigned d = tb + (unsigned)(h * NHALF);
+            umma_tf32(d, ahi, bhi, IDESC, s > 0 ? 1u : 0u);
+            umma_tf32(d, ahi, blo, IDESC, 1u);
+            umma_tf32(d, alo, bhi, IDESC, 1u);
+          }
+          tc_commit(&empty_bar[slot]);   // arrives when the MMAs above have finished reading the stage
+        }
+        tc_commit(&tmem_full_bar);       // ... and when the whole tile is accumulated
+      }
+    }
+  } else {
+    // =========================== epilogue (warps 0-3: TMEM lanes 32 w .. 32 w + 31) ===========================
+    const int pyl = lane >> 3, px = lane & 7;
+    const int m = warp * 32 + lane;                       // pixel within the tile == TMEM lane
+    const size_t bstride = out_bstride ? (size_t)out_bstride : (size_t)NP * HW;
+    const int Wb = (W + 7) >> 3;
+    int t = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+      const TileCoord tc = tile_coord(tile, tiles_x, tiles_y);
+      mbar_wait(&tmem_full_bar, t & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int bt = 0; bt < 3; ++bt) {   // 4 halo rows per load: rows 4 w + 4 bt .. + 3 (the warp's pixel rows need 4 w .. 4 w + 11)
+          unsigned r[32];
+          tmem_ld32(tb + ((unsigned)(warp * 32) << 16) + (unsigned)(h * NHALF + (warp * 4 + bt * 4) * 8), r);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int dy = bt * 4 + q - pyl;
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+              const int dx = 8 * h + cc - px;
+              if (dy >= 0 && dy < ND && dx >= 0 && dx < ND) staging[(dy * ND + dx) * PS + m] = __uint_as_float(r[q * 8 + cc]);
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty_bar[h]);   // this half of the accumulator may be overwritten by the next tile
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // coalesced copy-out: 81 planes x 32 float4 (4 pixels of one tile row each)
+      for (int idx = tid; idx < NP * 32; idx += 128) {
+        const int plane = idx >> 5, q4 = idx & 31;
+        const int row = q4 >> 1, xq = (q4 & 1) << 2;
+        const float4 v = *reinterpret_cast<const float4*>(staging + plane * PS + q4 * 4);
+        float e[4] = {v.x * inv_c, v.y * inv_c, v.z * inv_c, v.w * inv_c};
+        unsigned nib = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          nib |= (e[j] > 0.f ? 1u : 0u) << j;
+          e[j] = e[j] > 0.f ? e[j] : e[j] * slope;
+        }
+        const unsigned other = __shfl_xor_sync(0xffffffffu, nib, 1);   // idx and idx ^ 1 are the two halves of one 8-pixel row
+        const int y = tc.y0 + row, x = tc.x0 + xq;
+        if (y < H && x < W) {
+          if (mask != nullptr && xq == 0) mask[(((size_t)tc.b * NP + plane) * H + y) * Wb + (x >> 3)] = (unsigned char)(nib | (other << 4));
+          float* o = out + (size_t)tc.b * bstride + ((size_t)plane * H + y) * W + x;
+          if (VEC) *reinterpret_cast<float4*>(o) = make_float4(e[0], e[1], e[2], e[3]);
+          else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (x + j < W) o[j] = e[j];
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // staging tile free for the next tile
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "n"(TMEM_COLS));
+}
+
+}  // namespace
+
+int ocf_corr_fwd_tc_launch(const float* f1, const float* f2, float* out, unsigned char* mask_out, const float* norm, float* f1n_out,
+                           long long f1n_bstride, float* f2n_out, int B, int C, int H, int W, long long out_bstride, float leaky_slope,
+                           cudaStream_t s) {
+  const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
+  const long long ntiles = (long long)tiles_x * tiles_y * B;
+  if (ntiles > 0x7fffffffLL) return OCF_EUNSUPPORTED;
+  const bool vec = (W % 4 == 0) && ocf_aligned16(f1) && ocf_aligned16(f2) && ocf_aligned16(out) && (out_bstride % 4 == 0) &&
+                   (f1n_out == nullptr || (ocf_aligned16(f1n_out) && f1n_bstride % 4 == 0)) && (f2n_out == nullptr || ocf_aligned16(f2n_out));
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES;
+  auto kernel = vec ? corr_fwd_tc_kernel<true> : corr_fwd_tc_kernel<false>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[vec ? 1 : 0]) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set[vec ? 1 : 0] = true;
+  }
+  const int grid = ntiles < OCF_SM_COUNT ? (int)ntiles : OCF_SM_COUNT;
+  kernel<<<grid, THREADS, smem, s>>>(f1, f2, out, mask_out, norm, f1n_out, f1n_bstride, f2n_out, C, H, W, out_bstride, 1.0f / (float)C, leaky_slope,
+                                     tiles_x, tiles_y, (int)ntiles);
+  return ocf_launch_status();
+}

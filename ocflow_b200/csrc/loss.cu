@@ -346,17 +346,19 @@ occ_photo_fused_kernel(const float* __restrict__ img1, const float* __restrict__
   ocf_block_accumulate<6>(acc, sums);
 }
 
-// Quad version (W % 4 == 0, 16-byte aligned tensors): a thread owns 4 horizontally adjacent pixels.  When their 4 bilinear
-// samples are coherent (one tap-row pair, consecutive columns -- the normal case for a network flow) the 16 tap gathers
-// per channel become 4 x LDG.128 (two aligned groups per tap row) + a register funnel (common.cuh); otherwise the 16
-// scalar gathers are issued.  Compared with occ_photo_fused_kernel<4> this removes the 16 tap offsets + 16 validity flags
-// from the live state (126 -> about 64 registers, twice the resident warps) and 3/4 of the load instructions.
+// Quad version (W % 4 == 0, 16-byte aligned tensors, C == 3): a thread owns 4 horizontally adjacent pixels.  The kernel is
+// LATENCY bound (a pixel needs flow -> coordinates -> gathers -> loss: dependent DRAM round trips), so everything that does
+// not depend on the flow -- img1 (3 channels), range map, flow_gt, occ_gt -- is requested together with the flow, and the
+// gathers of all three channels are issued back to back: two exposed round trips per quad instead of six.  When the 4
+// bilinear samples are coherent (one tap-row pair, consecutive columns -- the normal case for a network flow) the 16 tap
+// gathers per channel are 4 x LDG.128 (two aligned groups per tap row) + a register funnel (common.cuh); otherwise the 16
+// scalar gathers are issued.
 template <int MINB>
 __global__ void __launch_bounds__(LT, MINB)
 occ_photo_quad_kernel(const float* __restrict__ img1, const float* __restrict__ img2, const float* __restrict__ flow,
                       const float* __restrict__ range, const float* __restrict__ flow_gt, const float* __restrict__ occ_gt,
-                      double* __restrict__ sums, float* __restrict__ dflow, float* __restrict__ warped, int C, int H, int W,
-                      float a2) {
+                      double* __restrict__ sums, float* __restrict__ dflow, float* __restrict__ warped, int H, int W, float a2) {
+  constexpr int C = 3;
   const int HW = H * W;
   const int gpi = HW >> 2;  // quads per image
   const int b = blockIdx.y;
@@ -367,14 +369,22 @@ occ_photo_quad_kernel(const float* __restrict__ img1, const float* __restrict__ 
   const float* fl_b = flow + (size_t)b * 2 * HW;
   const float* i1_b = img1 + (size_t)b * C * HW;
   const float* i2_b = img2 + (size_t)b * C * HW;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int gi = blockIdx.x * LT + threadIdx.x; gi < gpi; gi += gridDim.x * LT) {
     const int q = gi << 2;
     const int y = q / W, x = q - y * W;
+    // ---- round trip 1: the flow and everything that does not depend on it ----
     const float4 U4 = __ldg(reinterpret_cast<const float4*>(fl_b + q)), V4 = __ldg(reinterpret_cast<const float4*>(fl_b + HW + q));
+    float4 T1[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) T1[c] = ocf_ldg_stream4(i1_b + c * HW + q);
+    const float4 r4 = range != nullptr ? ocf_ldg_stream4(range + (size_t)b * HW + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 gu = flow_gt != nullptr ? ocf_ldg_stream4(flow_gt + (size_t)b * 2 * HW + q) : zero4;
+    const float4 gv = flow_gt != nullptr ? ocf_ldg_stream4(flow_gt + (size_t)b * 2 * HW + HW + q) : zero4;
+    const float4 p4 = occ_gt != nullptr ? ocf_ldg_stream4(occ_gt + (size_t)b * HW + q) : zero4;
     const float U[4] = {U4.x, U4.y, U4.z, U4.w}, V[4] = {V4.x, V4.y, V4.z, V4.w};
     int x0[4], y0[4];
-    float wx1[4], wy1[4];   // east / south weights; west = (x0 + 1) - ix is recomputed as 1 - wx1 only where exact (see below)
-    float wx0[4], wy0[4];
+    float wx0[4], wx1[4], wy0[4], wy1[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       // align_corners=True coordinates, reference op order (models/model.py:211-212 + ATen unnormalize); x*0.5f == x/2 exactly
@@ -389,69 +399,70 @@ occ_photo_quad_kernel(const float* __restrict__ img1, const float* __restrict__ 
     bool fast = x0[0] >= -8 && x0[0] <= W && y0[0] >= -2 && y0[0] <= H;
 #pragma unroll
     for (int i = 1; i < 4; ++i) fast = fast && y0[i] == y0[0] && x0[i] == x0[0] + i;
-    float e[4] = {0.f, 0.f, 0.f, 0.f}, gx[4] = {0.f, 0.f, 0.f, 0.f}, gy[4] = {0.f, 0.f, 0.f, 0.f};
-    // aligned-group plan of the coherent case
-    const int a = x0[0] & ~3, o = x0[0] - a;
-    const bool vn = y0[0] >= 0 && y0[0] < H, vs = y0[0] + 1 >= 0 && y0[0] + 1 < H;
-    const bool va = a >= 0 && a + 3 < W, vb = a + 4 >= 0 && a + 7 < W;
-    const int rowN = y0[0] * W + a;
-#pragma unroll 1
-    for (int c = 0; c < C; ++c) {
-      const float* ip = i2_b + c * HW;
-      const float4 t4 = __ldg(reinterpret_cast<const float4*>(i1_b + c * HW + q));
-      const float t1[4] = {t4.x, t4.y, t4.z, t4.w};
-      float ta[4], tb[4], tc[4], td[4];
-      if (fast) {
-        const float4 a0 = ldg4_or_zero(ip + rowN, vn && va), a1 = ldg4_or_zero(ip + rowN + 4, vn && vb);
-        const float4 b0 = ldg4_or_zero(ip + rowN + W, vs && va), b1 = ldg4_or_zero(ip + rowN + W + 4, vs && vb);
-        const float qn[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float qs[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    // ---- round trip 2: the gathers of all channels ----
+    float ta[C][4], tb[C][4], tc[C][4], td[C][4];
+    if (fast) {
+      const int a = x0[0] & ~3, o = x0[0] - a;
+      const bool vn = y0[0] >= 0 && y0[0] < H, vs = y0[0] + 1 >= 0 && y0[0] + 1 < H;
+      const bool va = a >= 0 && a + 3 < W, vb = a + 4 >= 0 && a + 7 < W;
+      const float* rp = i2_b + y0[0] * W + a;
+      float4 a0[C], a1[C], b0[C], b1[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        a0[c] = ldg4_or_zero(rp + c * HW, vn && va); a1[c] = ldg4_or_zero(rp + c * HW + 4, vn && vb);
+        b0[c] = ldg4_or_zero(rp + c * HW + W, vs && va); b1[c] = ldg4_or_zero(rp + c * HW + W + 4, vs && vb);
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float qn[8] = {a0[c].x, a0[c].y, a0[c].z, a0[c].w, a1[c].x, a1[c].y, a1[c].z, a1[c].w};
+        const float qs[8] = {b0[c].x, b0[c].y, b0[c].z, b0[c].w, b1[c].x, b1[c].y, b1[c].z, b1[c].w};
         float n5[5], s5[5];
         funnel_gather(qn, o, n5);
         funnel_gather(qs, o, s5);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { ta[i] = n5[i]; tb[i] = n5[i + 1]; tc[i] = s5[i]; td[i] = s5[i + 1]; }
-      } else {
+        for (int i = 0; i < 4; ++i) { ta[c][i] = n5[i]; tb[c][i] = n5[i + 1]; tc[c][i] = s5[i]; td[c][i] = s5[i + 1]; }
+      }
+    } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const bool vx0 = x0[i] >= 0 && x0[i] < W, vx1 = x0[i] + 1 >= 0 && x0[i] + 1 < W;
-          const bool vy0 = y0[i] >= 0 && y0[i] < H, vy1 = y0[i] + 1 >= 0 && y0[i] + 1 < H;
-          const int off = y0[i] * W + x0[i];
-          ta[i] = (vx0 && vy0) ? __ldg(ip + off) : 0.f; tb[i] = (vx1 && vy0) ? __ldg(ip + off + 1) : 0.f;
-          tc[i] = (vx0 && vy1) ? __ldg(ip + off + W) : 0.f; td[i] = (vx1 && vy1) ? __ldg(ip + off + W + 1) : 0.f;
+      for (int i = 0; i < 4; ++i) {
+        const bool vx0 = x0[i] >= 0 && x0[i] < W, vx1 = x0[i] + 1 >= 0 && x0[i] + 1 < W;
+        const bool vy0 = y0[i] >= 0 && y0[i] < H, vy1 = y0[i] + 1 >= 0 && y0[i] + 1 < H;
+        const int off = y0[i] * W + x0[i];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float* ip = i2_b + c * HW;
+          ta[c][i] = (vx0 && vy0) ? __ldg(ip + off) : 0.f; tb[c][i] = (vx1 && vy0) ? __ldg(ip + off + 1) : 0.f;
+          tc[c][i] = (vx0 && vy1) ? __ldg(ip + off + W) : 0.f; td[c][i] = (vx1 && vy1) ? __ldg(ip + off + W + 1) : 0.f;
         }
       }
+    }
+    float e[4] = {0.f, 0.f, 0.f, 0.f}, gx[4] = {0.f, 0.f, 0.f, 0.f}, gy[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float t1[4] = {T1[c].x, T1[c].y, T1[c].z, T1[c].w};
       float wv[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float sacc = 0.f;
-        sacc = fmaf(ta[i], wx0[i] * wy0[i], sacc); sacc = fmaf(tb[i], wx1[i] * wy0[i], sacc);
-        sacc = fmaf(tc[i], wx0[i] * wy1[i], sacc); sacc = fmaf(td[i], wx1[i] * wy1[i], sacc);
+        sacc = fmaf(ta[c][i], wx0[i] * wy0[i], sacc); sacc = fmaf(tb[c][i], wx1[i] * wy0[i], sacc);
+        sacc = fmaf(tc[c][i], wx0[i] * wy1[i], sacc); sacc = fmaf(td[c][i], wx1[i] * wy1[i], sacc);
         wv[i] = sacc;
         const float d = sacc - t1[i];
         const float r2 = fmaf(d, d, a2);
         const float inv = rsqrtf(r2);     // rho = r2 * inv, rho' = d * inv   (MUFU.RSQ, <= 2 ulp: far inside the loss tolerance)
         e[i] = fmaf(r2, inv, e[i]);
         const float gr = d * inv;
-        gx[i] = fmaf(gr, (tb[i] - ta[i]) * wy0[i] + (td[i] - tc[i]) * wy1[i], gx[i]);
-        gy[i] = fmaf(gr, (tc[i] - ta[i]) * wx0[i] + (td[i] - tb[i]) * wx1[i], gy[i]);
+        gx[i] = fmaf(gr, (tb[c][i] - ta[c][i]) * wy0[i] + (td[c][i] - tc[c][i]) * wy1[i], gx[i]);
+        gy[i] = fmaf(gr, (tc[c][i] - ta[c][i]) * wx0[i] + (td[c][i] - tb[c][i]) * wx1[i], gy[i]);
       }
       if (warped != nullptr) *reinterpret_cast<float4*>(warped + ((size_t)b * C + c) * HW + q) = make_float4(wv[0], wv[1], wv[2], wv[3]);
     }
+    const float r[4] = {r4.x, r4.y, r4.z, r4.w};
     float occv[4], vis[4];
-    if (range != nullptr) {
-      const float4 r4 = __ldg(reinterpret_cast<const float4*>(range + (size_t)b * HW + q));
-      const float r[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) occv[i] = 1.0f - fminf(fmaxf(r[i], 0.f), 1.f);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) occv[i] = 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) vis[i] = 1.0f - occv[i];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
+      occv[i] = range != nullptr ? 1.0f - fminf(fmaxf(r[i], 0.f), 1.f) : 0.f;
+      vis[i] = 1.0f - occv[i];
       acc[0] += e[i] * vis[i]; acc[1] += vis[i]; acc[2] += e[i] * occv[i]; acc[3] += occv[i];
     }
     if (dflow != nullptr) {
@@ -460,20 +471,15 @@ occ_photo_quad_kernel(const float* __restrict__ img1, const float* __restrict__ 
       *reinterpret_cast<float4*>(df + HW) = make_float4(gy[0] * vis[0] * cy, gy[1] * vis[1] * cy, gy[2] * vis[2] * cy, gy[3] * vis[3] * cy);
     }
     if (flow_gt != nullptr) {
-      const float4 gu = __ldg(reinterpret_cast<const float4*>(flow_gt + (size_t)b * 2 * HW + q));
-      const float4 gv = __ldg(reinterpret_cast<const float4*>(flow_gt + (size_t)b * 2 * HW + HW + q));
       const float gus[4] = {gu.x, gu.y, gu.z, gu.w}, gvs[4] = {gv.x, gv.y, gv.z, gv.w};
-      const float4 Ur = __ldg(reinterpret_cast<const float4*>(fl_b + q)), Vr = __ldg(reinterpret_cast<const float4*>(fl_b + HW + q));  // L1 hit
-      const float Uq[4] = {Ur.x, Ur.y, Ur.z, Ur.w}, Vq[4] = {Vr.x, Vr.y, Vr.z, Vr.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float du = Uq[i] - gus[i], dv = Vq[i] - gvs[i];
+        const float du = U[i] - gus[i], dv = V[i] - gvs[i];
         acc[4] += du * du + dv * dv;
       }
     }
     if (occ_gt != nullptr) {
       // F.binary_cross_entropy(input=occ_gt, target=occ_pred)  -- swapped on purpose, models/model.py:407
-      const float4 p4 = __ldg(reinterpret_cast<const float4*>(occ_gt + (size_t)b * HW + q));
       const float pin[4] = {p4.x, p4.y, p4.z, p4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -626,16 +632,17 @@ extern "C" int ocf_occ_photo_fused(const float* img1, const float* img2, const f
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   dim3 grid(bx, B);
-  if (vec && OCF_OPF_VPX == 4) {
+  if (vec && OCF_OPF_VPX == 4 && C == 3) {
     // one quad per thread (no grid-stride repetition needed up to the cap): enough CTAs for >= 6 per SM
     int qx = (gpi + LT - 1) / LT;
-    const int qcap = (8 * OCF_SM_COUNT + B - 1) / B;
+    static const int qcapn = []() { const char* e = getenv("OCF_OPF_QCAP"); return e ? atoi(e) : 8; }();
+    const int qcap = (qcapn * OCF_SM_COUNT + B - 1) / B;
     if (qx > qcap) qx = qcap;
     static const int minb = []() { const char* e = getenv("OCF_OPF_MINB"); return e ? atoi(e) : 2; }();   // developer knob (tuning runs)
     if (minb == 3)
-      occ_photo_quad_kernel<3><<<dim3(qx, B), LT, 0, s>>>(img1, img2, flow, range_map, flow_gt, occ_gt, sums, dflow_unit, warped_out, C, H, W, alpha * alpha);
+      occ_photo_quad_kernel<3><<<dim3(qx, B), LT, 0, s>>>(img1, img2, flow, range_map, flow_gt, occ_gt, sums, dflow_unit, warped_out, H, W, alpha * alpha);
     else
-      occ_photo_quad_kernel<2><<<dim3(qx, B), LT, 0, s>>>(img1, img2, flow, range_map, flow_gt, occ_gt, sums, dflow_unit, warped_out, C, H, W, alpha * alpha);
+      occ_photo_quad_kernel<2><<<dim3(qx, B), LT, 0, s>>>(img1, img2, flow, range_map, flow_gt, occ_gt, sums, dflow_unit, warped_out, H, W, alpha * alpha);
   } else if (vec)
     occ_photo_fused_kernel<OCF_OPF_VPX><<<grid, LT, 0, s>>>(img1, img2, flow, range_map, flow_gt, occ_gt, sums, dflow_unit, warped_out, C, H, W, alpha * alpha);
   else

@@ -32,7 +32,11 @@ struct PtrPack {
   float* out[MAX_T];
 };
 
-__device__ __forceinline__ void finalize_fwd(float* __restrict__ stats, int NG, double inv_len, int flags) {
+// The forward sums are taken about a per-group pivot (the group's first element): var = E[(x-p)^2] - E[x-p]^2 is shift
+// invariant and loses nothing to cancellation when |mean| >> std (the plain E[x^2] - mean^2 form from fp32 partial sums
+// does; torch.var_mean, which the reference uses, does not).
+__device__ __forceinline__ void finalize_fwd(float* __restrict__ stats, int NG, double inv_len, int flags, const PtrPack& pk, int BG,
+                                             size_t glen) {
   const volatile double* sums = reinterpret_cast<const volatile double*>(stats);  // written by other CTAs' atomics
   float* grp = stats + 4 * (size_t)NG;
   float* app = stats + 6 * (size_t)NG;
@@ -41,9 +45,12 @@ __device__ __forceinline__ void finalize_fwd(float* __restrict__ stats, int NG, 
   __syncthreads();
   double lm = 0.0, lv = 0.0;
   for (int g = threadIdx.x; g < NG; g += blockDim.x) {
-    const double m = sums[2 * g] * inv_len;
-    double v = sums[2 * g + 1] * inv_len - m * m;
+    const int t = g / BG;
+    const double pivot = (double)pk.in[t][(size_t)(g - t * BG) * glen];
+    const double ms = sums[2 * g] * inv_len;          // mean of (x - pivot)
+    double v = sums[2 * g + 1] * inv_len - ms * ms;
     if (v < 0.0) v = 0.0;
+    const double m = pivot + ms;
     grp[2 * g] = (float)m;
     grp[2 * g + 1] = (float)v;
     lm += m; lv += v;
@@ -99,6 +106,7 @@ group_sums_kernel(PtrPack pk, int B, int G, size_t glen, float* __restrict__ ws,
   const int t = gidx / (B * G), rem = gidx - t * (B * G);
   const float* x = pk.in[t] + (size_t)rem * glen;
   const float* w = SECOND ? pk.in2[t] + (size_t)rem * glen : nullptr;
+  const float pivot = SECOND ? 0.f : __ldg(x);   // forward: sums of (x - pivot), see finalize_fwd
   float acc[2] = {0.f, 0.f};
   if (VEC) {
     const size_t n4 = glen / 4;
@@ -107,7 +115,11 @@ group_sums_kernel(PtrPack pk, int B, int G, size_t glen, float* __restrict__ ws,
     float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;  // two independent chains per sum
     size_t i = lo + threadIdx.x;
     for (; i + NT < hi; i += 2 * NT) {
-      const float4 u = ocf_ldg_stream4(x + 4 * i), v = ocf_ldg_stream4(x + 4 * (i + NT));
+      float4 u = ocf_ldg_stream4(x + 4 * i), v = ocf_ldg_stream4(x + 4 * (i + NT));
+      if (!SECOND) {
+        u.x -= pivot; u.y -= pivot; u.z -= pivot; u.w -= pivot;
+        v.x -= pivot; v.y -= pivot; v.z -= pivot; v.w -= pivot;
+      }
       float4 p = u, q = v;
       if (SECOND) { p = ocf_ldg_stream4(w + 4 * i); q = ocf_ldg_stream4(w + 4 * (i + NT)); }
       a0 += (u.x + u.y) + (u.z + u.w);
@@ -116,7 +128,8 @@ group_sums_kernel(PtrPack pk, int B, int G, size_t glen, float* __restrict__ ws,
       b1 = fmaf(v.x, q.x, fmaf(v.y, q.y, fmaf(v.z, q.z, fmaf(v.w, q.w, b1))));
     }
     if (i < hi) {
-      const float4 u = ocf_ldg_stream4(x + 4 * i);
+      float4 u = ocf_ldg_stream4(x + 4 * i);
+      if (!SECOND) { u.x -= pivot; u.y -= pivot; u.z -= pivot; u.w -= pivot; }
       float4 p = u;
       if (SECOND) p = ocf_ldg_stream4(w + 4 * i);
       a0 += (u.x + u.y) + (u.z + u.w);
@@ -128,7 +141,7 @@ group_sums_kernel(PtrPack pk, int B, int G, size_t glen, float* __restrict__ ws,
     const size_t per = (glen + gridDim.x - 1) / gridDim.x;
     const size_t lo = (size_t)blockIdx.x * per, hi = min(glen, lo + per);
     for (size_t i = lo + threadIdx.x; i < hi; i += NT) {
-      const float a = x[i];
+      const float a = x[i] - pivot;
       const float bb = SECOND ? w[i] : a;
       acc[0] += a;
       acc[1] = fmaf(a, bb, acc[1]);
@@ -144,7 +157,7 @@ group_sums_kernel(PtrPack pk, int B, int G, size_t glen, float* __restrict__ ws,
   if (!last) return;
   __threadfence();
   if (SECOND) finalize_bwd(stats_for_bwd, ws, NG, (double)glen, flags);
-  else finalize_fwd(ws, NG, 1.0 / (double)glen, flags);
+  else finalize_fwd(ws, NG, 1.0 / (double)glen, flags, pk, B * G, glen);
 }
 
 // y = (x - m) * r per group.  grid: (chunks, NG)
@@ -205,9 +218,10 @@ int chunks_for(size_t glen, int NG) {
 
 }  // namespace
 
-extern "C" int ocf_normalize_fwd(const float* const* xs, float* const* ys, int T, int B, int C, int H, int W, int flags, float* stats,
-                                 ocf_stream_t stream) {
-  OCF_REQUIRE_PTR(xs); OCF_REQUIRE_PTR(ys); OCF_REQUIRE_PTR(stats);
+// statistics only: fills the stats workspace (per-group {mean, var} and the applied {mean, inv_std}); the apply pass is either
+// norm_apply_kernel (ocf_normalize_fwd) or folded into the consumer (ocf_level_corr_fwd normalises on load)
+extern "C" int ocf_normalize_stats(const float* const* xs, int T, int B, int C, int H, int W, int flags, float* stats, ocf_stream_t stream) {
+  OCF_REQUIRE_PTR(xs); OCF_REQUIRE_PTR(stats);
   OCF_REQUIRE(T > 0 && T <= MAX_T, OCF_EUNSUPPORTED);
   OCF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, OCF_ESHAPE);
   OCF_REQUIRE((flags & ~15) == 0, OCF_EUNSUPPORTED);
@@ -215,9 +229,9 @@ extern "C" int ocf_normalize_fwd(const float* const* xs, float* const* ys, int T
   PtrPack pk;
   bool vec = true;
   for (int t = 0; t < T; ++t) {
-    OCF_REQUIRE_PTR(xs[t]); OCF_REQUIRE_PTR(ys[t]);
-    pk.in[t] = xs[t]; pk.in2[t] = nullptr; pk.out[t] = ys[t];
-    vec = vec && ocf_aligned16(xs[t]) && ocf_aligned16(ys[t]);
+    OCF_REQUIRE_PTR(xs[t]);
+    pk.in[t] = xs[t]; pk.in2[t] = nullptr; pk.out[t] = nullptr;
+    vec = vec && ocf_aligned16(xs[t]);
   }
   const int G = (flags & OCF_NORM_ACROSS_CHANNELS) ? 1 : C;
   const size_t glen = (size_t)(G == 1 ? C : 1) * H * W;
@@ -232,8 +246,25 @@ extern "C" int ocf_normalize_fwd(const float* const* xs, float* const* ys, int T
   const int chunks = chunks_for(glen, NG);
   if (vec) group_sums_kernel<false, true><<<dim3(chunks, NG), NT, 0, s>>>(pk, B, G, glen, stats, ticket, nullptr, NG, flags);
   else group_sums_kernel<false, false><<<dim3(chunks, NG), NT, 0, s>>>(pk, B, G, glen, stats, ticket, nullptr, NG, flags);
-  if (int st = ocf_launch_status()) return st;
-  norm_apply_kernel<<<dim3(chunks, NG), NT, 0, s>>>(pk, B, G, glen, stats + 6 * (size_t)NG, vec);
+  return ocf_launch_status();
+}
+
+extern "C" int ocf_normalize_fwd(const float* const* xs, float* const* ys, int T, int B, int C, int H, int W, int flags, float* stats,
+                                 ocf_stream_t stream) {
+  OCF_REQUIRE_PTR(ys);
+  if (int st = ocf_normalize_stats(xs, T, B, C, H, W, flags, stats, stream)) return st;
+  PtrPack pk;
+  bool vec = true;
+  for (int t = 0; t < T; ++t) {
+    OCF_REQUIRE_PTR(ys[t]);
+    pk.in[t] = xs[t]; pk.in2[t] = nullptr; pk.out[t] = ys[t];
+    vec = vec && ocf_aligned16(xs[t]) && ocf_aligned16(ys[t]);
+  }
+  const int G = (flags & OCF_NORM_ACROSS_CHANNELS) ? 1 : C;
+  const size_t glen = (size_t)(G == 1 ? C : 1) * H * W;
+  const int NG = T * B * G;
+  vec = vec && (glen % 4 == 0);
+  norm_apply_kernel<<<dim3(chunks_for(glen, NG), NG), NT, 0, ocf_cast_stream(stream)>>>(pk, B, G, glen, stats + 6 * (size_t)NG, vec);
   return ocf_launch_status();
 }
 

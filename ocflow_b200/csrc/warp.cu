@@ -628,7 +628,7 @@ int pick_slab(int C, int HW, int B) {
 
 // developer knob for tuning runs: OCF_WARP_QUAD bit 0 = forward, bit 1 = backward, bit 2 = range map ; OCF_QUAD_CTAS = CTAs per SM aimed at
 int quad_mask() {
-  static const int m = []() { const char* e = getenv("OCF_WARP_QUAD"); return e ? atoi(e) : 1; }();
+  static const int m = []() { const char* e = getenv("OCF_WARP_QUAD"); return e ? atoi(e) : 0; }();
   return m;
 }
 int quad_ctas() {

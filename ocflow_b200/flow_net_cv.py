@@ -4,9 +4,11 @@ Same constructor (`FlowNetCV(displacement=4)`), same parameter names/shapes and 
 checkpoint loads unchanged and `torch.manual_seed(s)` yields the reference's initial weights), same forward contract:
 `forward(x[B,6,H,W]) -> (flow1 [B,2,H,W] pixels, flow_l2 [B,2,H/4,W/4] quarter-res pixels)`.
 
-Per pyramid level the reference runs warp -> normalize_features -> compute_cost_volume -> LeakyReLU as ~1000 ATen
-launches; here it is 5 launches of our kernels (warp with the `up_flow*scale` folded in, 3-kernel normalisation,
-correlation with the LeakyReLU fused).  The convolution stacks stay on cuDNN (out of scope).
+Per pyramid level the reference runs warp -> normalize_features -> compute_cost_volume -> LeakyReLU -> cat as ~1000 ATen
+launches; here it is ONE fused op of 3 launches (`ops.level_fused`: warp with the `up_flow*scale` folded in, one
+statistics pass, and a tensor-core correlation that normalises its operands on load and writes the cost volume and the
+normalised c1 straight into the decoder's concat buffer).  The convolution stacks stay on cuDNN (out of scope, SURVEY.md
+section 2).
 """
 import torch
 import torch.nn as nn
@@ -76,7 +78,15 @@ class FlowNetCV(nn.Module):
             feats[lvl] = t
         return feats
 
+    # hparams-free switch (not a reference hyper-parameter): False runs the level as 5 separate ops + torch.cat
+    fused_level = True
+
     def _level(self, lvl, c1, c2, up_flow, up_feat):
+        if self.fused_level and self.displacement == 4:
+            x = ops.level_fused(c1, c2, up_flow, up_feat, flow_scale=_WARP_SCALE.get(lvl, 1.0), leaky_slope=0.1)
+            for i in range(5):
+                x = torch.cat((getattr(self, "conv%d_%d" % (lvl, i))(x), x), 1)
+            return x, getattr(self, "predict_flow%d" % lvl)(x)
         if lvl < 6:
             c2 = ops.warp(c2, up_flow, align_corners=False, flow_scale=_WARP_SCALE[lvl])
         c1, c2 = ops.normalize_features([c1, c2])

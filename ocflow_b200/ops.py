@@ -157,6 +157,101 @@ def normalize_features(feature_list, normalize=True, center=True, moments_across
 
 
 # -------------------------------------------------------------------------------------------------
+# fused FlowNetCV pyramid level: warp -> normalize_features -> compute_cost_volume -> LeakyReLU -> cat
+# (cost_volume_flow_net.py:171-173 and 186-190 / 201-205 / 216-220 / 231-235)
+# -------------------------------------------------------------------------------------------------
+_NORM_DEFAULT = NORM_NORMALIZE | NORM_CENTER | NORM_ACROSS_CHANNELS | NORM_ACROSS_IMAGES
+
+
+class _LevelFused(torch.autograd.Function):
+    """x = cat(LeakyReLU(corr(c1n, c2n)), c1n[, up_flow, up_feat]) with [c1n, c2n] = normalize_features([c1, warp(c2, up_flow*scale)]).
+
+    3 launches forward (warp, statistics, tensor-core correlation normalising on load and writing corr + c1n straight into
+    the concat buffer) instead of 5 + torch.cat; the normalised tensors are never re-read and the two widest pieces of the
+    concat are never copied.  Backward: correlation backward (c1n read in place from the buffer), the normalisation
+    backward through the statistics, the warp backward."""
+
+    @staticmethod
+    def forward(ctx, c1, c2, up_flow, up_feat, scale, slope):
+        B, C, H, W = c1.shape
+        has_flow = up_flow is not None
+        # coarsest level (cost_volume_flow_net.py:171-176): the decoder input is the cost volume alone
+        width = 81 + C + up_flow.shape[1] + up_feat.shape[1] if has_flow else 81
+        X = torch.empty((B, width, H, W), device=c1.device, dtype=torch.float32)
+        with torch.cuda.device_of(c1):
+            if has_flow:
+                w2 = torch.empty_like(c2)
+                _lib.call("ocf_warp_fwd", _p(c2), _p(up_flow), None, _p(w2), B, C, H, W, 0, float(scale), _stream())
+            else:
+                w2 = c2
+            NG = 2 * B
+            stats = torch.empty(8 * NG + 8, device=c1.device, dtype=torch.float32)
+            _lib.call("ocf_normalize_stats", ctypes.cast(_ptr_array([c1, w2]), ctypes.c_void_p), 2, B, C, H, W, _NORM_DEFAULT, _p(stats), _stream())
+            f2n = torch.empty_like(c2)
+            mask = torch.empty((B, 81, H, (W + 7) // 8), device=c1.device, dtype=torch.uint8)
+            f1n = X[:, 81:81 + C] if has_flow else torch.empty_like(c1)
+            norm = stats[6 * NG:6 * NG + 2]      # {mean, inv_std}: one scalar pair for all groups (moments_across_images)
+            _lib.call("ocf_level_corr_fwd", _p(c1), _p(w2), _p(norm), _p(X), X.stride(0), _p(f1n), f1n.stride(0), _p(f2n), _p(mask),
+                      B, C, H, W, float(slope), _stream())
+            if has_flow:
+                X[:, 81 + C:81 + C + up_flow.shape[1]].copy_(up_flow)
+                X[:, 81 + C + up_flow.shape[1]:].copy_(up_feat)
+        ctx.cfg = (float(scale), float(slope), has_flow, up_flow.shape[1] if has_flow else 0)
+        ctx.save_for_backward(c1, c2, up_flow if has_flow else c1.new_empty(0), w2, f2n, mask, stats, X if has_flow else f1n)
+        return X
+
+    @staticmethod
+    def backward(ctx, gX):
+        c1, c2, up_flow, w2, f2n, mask, stats, keep = ctx.saved_tensors
+        scale, slope, has_flow, nflow = ctx.cfg
+        B, C, H, W = c1.shape
+        NG = 2 * B
+        if not (gX.stride(3) == 1 and gX.stride(2) == W and gX.stride(1) == H * W and gX.stride(0) % 4 == 0 and gX.data_ptr() % 16 == 0):
+            gX = gX.contiguous()
+        f1n = keep[:, 81:81 + C] if has_flow else keep
+        dfn1 = torch.empty_like(c1)
+        dfn2 = torch.empty_like(c2)
+        with torch.cuda.device_of(c1):
+            _lib.call("ocf_level_corr_bwd", _p(gX), gX.stride(0), _p(mask), _p(f1n), f1n.stride(0), _p(f2n), _p(dfn1), _p(dfn2), B, C, H, W,
+                      slope, _stream())
+            if has_flow:
+                dfn1.add_(gX[:, 81:81 + C])      # c1n is also an output (concatenated into the decoder input)
+            dc1 = torch.empty_like(c1)
+            dw2 = torch.empty_like(c2)
+            red = torch.empty(8 * NG, device=c1.device, dtype=torch.float32)
+            _lib.call("ocf_normalize_bwd", ctypes.cast(_ptr_array([dfn1, dfn2]), ctypes.c_void_p), ctypes.cast(_ptr_array([c1, w2]), ctypes.c_void_p),
+                      ctypes.cast(_ptr_array([dc1, dw2]), ctypes.c_void_p), 2, B, C, H, W, _NORM_DEFAULT, _p(stats), _p(red), _stream())
+            if not has_flow:
+                return dc1, dw2, None, None, None, None
+            need_c2, need_flow = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+            dc2 = torch.empty_like(c2) if need_c2 else None
+            dflow = torch.empty_like(up_flow) if need_flow else None
+            if need_c2 or need_flow:
+                _lib.call("ocf_warp_bwd", _p(dw2), _p(c2), _p(up_flow), None, _p(dc2), _p(dflow), None, B, C, H, W, 0, scale, _stream())
+            if need_flow:
+                dflow.add_(gX[:, 81 + C:81 + C + nflow])
+            dfeat = gX[:, 81 + C + nflow:] if ctx.needs_input_grad[3] else None
+        return dc1, dc2, dflow, dfeat, None, None
+
+
+def level_fused(c1, c2, up_flow=None, up_feat=None, flow_scale=1.0, leaky_slope=0.1):
+    """One FlowNetCV decoder level input (d = 4): see _LevelFused.  up_flow / up_feat are None at the coarsest level."""
+    c1 = _req(c1, "c1", 4)
+    c2 = _req(c2, "c2", 4)
+    if c1.shape != c2.shape:
+        raise ValueError("c1 and c2 must have the same shape")
+    if (up_flow is None) != (up_feat is None):
+        raise ValueError("up_flow and up_feat go together")
+    if up_flow is not None:
+        up_flow = _req(up_flow, "up_flow", 4)
+        up_feat = _req(up_feat, "up_feat", 4)
+        B, C, H, W = c1.shape
+        if up_flow.shape != (B, 2, H, W) or up_feat.shape[0] != B or up_feat.shape[2:] != (H, W):
+            raise ValueError("up_flow must be [B,2,H,W] and up_feat [B,*,H,W] matching c1")
+    return _LevelFused.apply(c1, c2, up_flow, up_feat, float(flow_scale), float(leaky_slope))
+
+
+# -------------------------------------------------------------------------------------------------
 # bilinear backward warp
 # -------------------------------------------------------------------------------------------------
 class _Warp(torch.autograd.Function):
@@ -532,8 +627,10 @@ class _OccPhotoFused(torch.autograd.Function):
         den_occ = sums[3] * 3 + 1e-16
         photo = (sums[0] / den_vis).to(torch.float32)
         photo_occ = (sums[2] / den_occ).to(torch.float32)
-        mse = (sums[4] / float(B * 2 * H * W)).to(torch.float32)
-        bce = (sums[5] / float(B * H * W)).to(torch.float32)
+        # terms whose ground truth is absent are NaN, not 0.0 (a zero would read as a perfect score)
+        nan = float("nan")
+        mse = (sums[4] / float(B * 2 * H * W)).to(torch.float32) if flow_gt is not None else sums[4].to(torch.float32) * 0 + nan
+        bce = (sums[5] / float(B * H * W)).to(torch.float32) if occ_gt is not None else sums[5].to(torch.float32) * 0 + nan
         if need:
             ctx.save_for_backward(dflow, den_vis)
         ctx.mark_non_differentiable(photo_occ, mse, bce)
@@ -552,6 +649,10 @@ def occ_photo_fused(img1, img2, flow, rmap=None, flow_gt=None, occ_gt=None, alph
     img1 = _req(img1.detach(), "img1", 4)
     img2 = _req(img2.detach(), "img2", 4)
     flow = _req(flow, "flow", 4)
+    if img1.shape[1] != 3 or img2.shape != img1.shape:
+        # the denominators carry the reference's literal 3 (models/model.py:43): the equivalence with photometric_error /
+        # torch.mean only holds for 3-channel images
+        raise ValueError("occ_photo_fused expects two [B,3,H,W] images (got %s and %s)" % (tuple(img1.shape), tuple(img2.shape)))
     rmap = None if rmap is None else _req(rmap.detach(), "range_map", 4)
     flow_gt = None if flow_gt is None else _req(flow_gt.detach(), "flow_gt", 4)
     occ_gt = None if occ_gt is None else _req(occ_gt.detach(), "occ_gt", 4)

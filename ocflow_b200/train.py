@@ -74,13 +74,24 @@ class TrainStep:
 
     def _capture(self, batch):
         self.static_batch = tuple(t.clone() for t in batch)
+        # The warm-up runs real steps (cuDNN autotune, lazy module loads, Adam state allocation).  Weights and optimizer
+        # state are snapshotted before and restored after it, so the captured trajectory is exactly the eager one: one
+        # update per batch, Adam's step count starting at 0 (the reference / use_graph=False behaviour).
+        model_state = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(3):  # warm-up on a side stream: cuDNN autotune, lazy module loads, Adam state
+            for _ in range(3):
                 self._eager(self.static_batch)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        with torch.no_grad():
+            for k, v in self.model.state_dict().items():
+                v.copy_(model_state[k])
+            for st in self.opt.state.values():   # keep the (capturable, device-resident) state tensors, reset their contents
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.static_loss = self._eager(self.static_batch)

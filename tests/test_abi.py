@@ -26,7 +26,7 @@ def test_header_declares_and_library_exports_every_symbol():
     lib = _lib.load()
     for name in decl:
         assert hasattr(lib, name), "libocflow_b200.so does not export %s" % name
-    assert lib.ocf_abi_version() == 2
+    assert lib.ocf_abi_version() == 3
     assert lib.ocf_build_sm() == 100
     assert b"OCF_ENULL" in lib.ocf_error_string(-1)
 

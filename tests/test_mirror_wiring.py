@@ -47,6 +47,15 @@ def _oracle_ops():
         assert kind == ns.PAIR_MSE
         return ((a - b) ** 2).mean()
 
+    def level_fused(c1, c2, up_flow=None, up_feat=None, flow_scale=1.0, leaky_slope=0.1):
+        # what ops.level_fused computes, spelled with the oracle's functions (cost_volume_flow_net.py:186-190)
+        if up_flow is not None:
+            c2 = O.warp(c2, up_flow * flow_scale, False)
+        c1n, c2n = O.normalize_features([c1, c2])
+        corr = torch.nn.functional.leaky_relu(O.cost_volume(c1n, c2n, 4), leaky_slope)
+        return corr if up_flow is None else torch.cat((corr, c1n, up_flow, up_feat), 1)
+
+    ns.level_fused = level_fused
     ns.warp, ns.cost_volume, ns.range_map, ns.occ_photo_fused = warp, cost_volume, range_map, occ_photo_fused
     ns.smoothness_loss, ns.pair_loss = smoothness_loss, pair_loss
     ns.normalize_features = lambda fl, **kw: O.normalize_features(fl, **kw)
