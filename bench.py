@@ -245,20 +245,24 @@ def kernel_table(args, torch):
         d1, d2 = torch.empty_like(f1), torch.empty_like(f2)
         wout = torch.empty_like(f2)
         dfl = torch.empty_like(fl)
-        table["corr_fwd_L%d" % lvl] = (lambda f1=f1, f2=f2, out=out, msk=msk, C=C, h=h, w=w: _lib.call(
-            "ocf_corr_fwd", P(f1), P(f2), P(out), B, C, h, w, 4, 0, 0.1, None, P(msk), st), 4 * n * (2 * C + 81) + n * 81 // 8, 2)
-        table["corr_bwd_L%d" % lvl] = (lambda gout=gout, msk=msk, f1=f1, f2=f2, d1=d1, d2=d2, C=C, h=h, w=w: _lib.call(
-            "ocf_corr_bwd", P(gout), None, P(f1), P(f2), P(d1), P(d2), B, C, h, w, 4, 0, 0, 0.1, P(msk), st), 4 * n * (81 + 4 * C) + n * 81 // 8, 1)
-        # normalisation of the two feature maps of the level (3 kernels fwd, 3 kernels bwd)
+        f1n, f2n = torch.empty_like(f1), torch.empty_like(f2)
+        # what the step runs per level (ops.level_fused): statistics pass, tensor-core correlation normalising on load (writes
+        # corr, c1n, c2n and the sign bitmask), then in the backward the correlation / normalisation / warp backward kernels
         y1, y2 = torch.empty_like(f1), torch.empty_like(f2)
         stats = torch.empty(8 * 2 * B + 8, device=dev)
         red = torch.empty(8 * 2 * B, device=dev)
         xs_arr = (ctypes.c_void_p * 2)(f1.data_ptr(), f2.data_ptr())
         ys_arr = (ctypes.c_void_p * 2)(y1.data_ptr(), y2.data_ptr())
         gs_arr = (ctypes.c_void_p * 2)(d1.data_ptr(), d2.data_ptr())
-        table["normalize_fwd_L%d" % lvl] = (lambda xs_arr=xs_arr, ys_arr=ys_arr, stats=stats, C=C, h=h, w=w: _lib.call(
-            "ocf_normalize_fwd", ctypes.cast(xs_arr, ctypes.c_void_p), ctypes.cast(ys_arr, ctypes.c_void_p), 2, B, C, h, w, 15, P(stats), st),
-            4 * n * 2 * C * 3, 2)
+        _lib.call("ocf_normalize_stats", ctypes.cast(xs_arr, ctypes.c_void_p), 2, B, C, h, w, 15, P(stats), st)
+        norm_ptr = ctypes.c_void_p(stats.data_ptr() + 4 * 6 * 2 * B)
+        table["normalize_stats_L%d" % lvl] = (lambda xs_arr=xs_arr, stats=stats, C=C, h=h, w=w: _lib.call(
+            "ocf_normalize_stats", ctypes.cast(xs_arr, ctypes.c_void_p), 2, B, C, h, w, 15, P(stats), st), 4 * n * 2 * C, 2)
+        table["level_corr_fwd_L%d" % lvl] = (lambda f1=f1, f2=f2, out=out, msk=msk, f1n=f1n, f2n=f2n, norm_ptr=norm_ptr, C=C, h=h, w=w: _lib.call(
+            "ocf_level_corr_fwd", P(f1), P(f2), norm_ptr, P(out), 0, P(f1n), 0, P(f2n), P(msk), B, C, h, w, 0.1, st),
+            4 * n * (4 * C + 81) + n * 81 // 8, 2)
+        table["level_corr_bwd_L%d" % lvl] = (lambda gout=gout, msk=msk, f1=f1, f2=f2, d1=d1, d2=d2, C=C, h=h, w=w: _lib.call(
+            "ocf_level_corr_bwd", P(gout), 0, P(msk), P(f1), 0, P(f2), P(d1), P(d2), B, C, h, w, 0.1, st), 4 * n * (81 + 4 * C) + n * 81 // 8, 1)
         table["normalize_bwd_L%d" % lvl] = (lambda xs_arr=xs_arr, ys_arr=ys_arr, gs_arr=gs_arr, stats=stats, red=red, C=C, h=h, w=w: _lib.call(
             "ocf_normalize_bwd", ctypes.cast(ys_arr, ctypes.c_void_p), ctypes.cast(xs_arr, ctypes.c_void_p), ctypes.cast(gs_arr, ctypes.c_void_p),
             2, B, C, h, w, 15, P(stats), P(red), st), 4 * n * 2 * C * 4, 1)
@@ -318,6 +322,90 @@ def time_kernels(args, torch, with_copy_ref=False):
     return res
 
 
+def extra_kernel_rows(args, torch, peak):
+    """Driver-visible kernel numbers beyond the step's own shapes (BASELINE.json configs 4 and 5), same harness as
+    time_kernels (kernel alone, 1 GiB L2 flush before every launch): KITTI pyramid level 188x621 (ragged rows) at B = 8 for
+    C in {32, 128} -- correlation forward / backward and warp forward / backward through the C ABI -- and the Sintel 436x1024
+    occlusion pipeline (range map -> mask -> fused Charbonnier -> census + SSIM -> backward to the flow)."""
+    import ctypes
+
+    from ocflow_b200 import _lib
+
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    flush = torch.empty(1024 * 1024 * 1024 // 4, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(7)
+
+    def P(t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    def timed(fn, reps=6):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        return statistics.mean(ts)
+
+    rows = {}
+    B, h, w = 8, 188, 621
+    n = B * h * w
+    for C in (32, 128):
+        f1 = torch.randn(B, C, h, w, device="cuda", generator=g)
+        f2 = torch.randn(B, C, h, w, device="cuda", generator=g)
+        import torch.nn.functional as F
+        fl = F.interpolate(torch.randn(B, 2, h // 4, w // 4, device="cuda", generator=g) * 2, size=(h, w), mode="bilinear", align_corners=True).contiguous()
+        out = torch.empty(B, 81, h, w, device="cuda")
+        gout = torch.randn(B, 81, h, w, device="cuda", generator=g)
+        msk = torch.zeros(B, 81, h, (w + 7) // 8, device="cuda", dtype=torch.uint8)
+        d1, d2, wout, dfl = torch.empty_like(f1), torch.empty_like(f2), torch.empty_like(f2), torch.empty_like(fl)
+        cases = {
+            "corr_fwd": (lambda: _lib.call("ocf_corr_fwd", P(f1), P(f2), P(out), B, C, h, w, 4, 0, 0.1, None, P(msk), st), 4 * n * (2 * C + 81), 2 * 81 * C * n),
+            "corr_bwd": (lambda: _lib.call("ocf_corr_bwd", P(gout), None, P(f1), P(f2), P(d1), P(d2), B, C, h, w, 4, 0, 0, 0.1, P(msk), st), 4 * n * (81 + 4 * C), 4 * 81 * C * n),
+            "warp_fwd": (lambda: _lib.call("ocf_warp_fwd", P(f2), P(fl), None, P(wout), B, C, h, w, 0, 1.25, st), 4 * n * (2 * C + 2), 0),
+            "warp_bwd": (lambda: _lib.call("ocf_warp_bwd", P(wout), P(f2), P(fl), None, P(d2), P(dfl), None, B, C, h, w, 0, 1.25, st), 4 * n * (3 * C + 4), 0),
+        }
+        for name, (fn, nbytes, flops) in cases.items():
+            t = timed(fn)
+            rows["kitti_188x621_B8_C%d_%s" % (C, name)] = {"us": round(t * 1e6, 1), "gbs": round(nbytes / t / 1e9, 1), "frac": round(nbytes / t / 1e9 / peak, 3),
+                                                          "tflops": round(flops / t / 1e12, 2) if flops else None}
+        del f1, f2, out, gout, msk, d1, d2, wout, dfl
+    # config 4
+    import ocflow_b200 as ocf
+    from ocflow_b200 import ops
+
+    B, H, W = 8, 436, 1024
+    n = B * H * W
+    img1 = torch.rand(B, 3, H, W, device="cuda", generator=g) * 2 - 1
+    img2 = torch.rand(B, 3, H, W, device="cuda", generator=g) * 2 - 1
+    fw = (torch.randn(B, 2, H, W, device="cuda", generator=g) * 8).requires_grad_(True)
+    bw = -fw.detach() + torch.randn(B, 2, H, W, device="cuda", generator=g) * 0.5
+
+    def whole():
+        with torch.no_grad():
+            rmap, occ = ops.range_map(bw, with_occlusion=True)
+        photo, _, _, _ = ops.occ_photo_fused(img1, img2, fw, rmap)
+        warped = ops.warp(img2, fw, align_corners=True)
+        total = photo + ocf.census_loss(warped, img1, occ, 3) + ocf.ssim_photometric_loss(warped, img1, 11)
+        return torch.autograd.grad(total, fw)
+
+    t = timed(whole)
+    rows["sintel_436x1024_B8_occlusion_pipeline_fwd_bwd"] = {"us": round(t * 1e6, 1), "pairs_per_s": round(B / t, 1)}
+    with torch.no_grad():
+        rmap = ops.range_map(bw)
+    for name, fn, nbytes in (("range_map", lambda: ops.range_map(bw), 4 * n * 4),
+                             ("occ_photo_fused", lambda: ops.occ_photo_fused(img1, img2, fw.detach().requires_grad_(True), rmap), 4 * n * 14)):
+        t = timed(fn)
+        rows["sintel_436x1024_B8_" + name] = {"us": round(t * 1e6, 1), "gbs": round(nbytes / t / 1e9, 1), "frac": round(nbytes / t / 1e9 / peak, 3)}
+    return rows
+
+
 def live_kernel_times(step, batch, torch, height, reps=3):
     """Per-kernel durations measured LIVE inside real training steps: the same step run eagerly (a CUDA graph replay
     cannot carry events) with every C-ABI call bracketed by CUDA events on the stream it is enqueued on.  Returns
@@ -329,14 +417,13 @@ def live_kernel_times(step, batch, torch, height, reps=3):
     def level(h):
         return int(round(math.log2(height / float(h)))) if h > 0 else 0
 
+    H_INDEX = {"ocf_corr_fwd": 2, "ocf_corr_bwd": 2, "ocf_normalize_fwd": 3, "ocf_normalize_bwd": 3, "ocf_normalize_stats": 3,
+               "ocf_warp_fwd": 2, "ocf_warp_bwd": 2, "ocf_level_corr_fwd": 4, "ocf_level_corr_bwd": 4}
+
     def classify(name, ints):
         short = name[4:]
-        if name in ("ocf_corr_fwd", "ocf_corr_bwd"):
-            return "%s_L%d" % (short, level(ints[2]))
-        if name in ("ocf_normalize_fwd", "ocf_normalize_bwd"):
-            return "%s_L%d" % (short, level(ints[3]))
-        if name in ("ocf_warp_fwd", "ocf_warp_bwd"):
-            return "%s_L%d" % (short, level(ints[2]))
+        if name in H_INDEX:
+            return "%s_L%d" % (short, level(ints[H_INDEX[name]]))
         return short
 
     step._eager(batch)
@@ -582,8 +669,9 @@ def main():
         # live pass: inside real steps, CUDA events on the launching stream (N=1 only: the eager step of a multi-rank job
         # contains the all-reduce, which rank 0 cannot run alone)
         live = live_kernel_times(step, batch, torch, H) if world == 1 else {k: (v["us"], v["per_step"]) for k, v in kt.items()}
-        known = [k for k in live if k in kt]
-        dom = max(known, key=lambda k: live[k][0] * live[k][1])
+        # the SAME kernel at every N: the one with the largest isolated time per step (the live pass exists at N = 1 only)
+        known = [k for k in kt if kt[k]["per_step"] > 0 and (world > 1 or k in live)]
+        dom = max(known, key=lambda k: kt[k]["us"] * kt[k]["per_step"])
         us = live[dom][0]
         gbs = kt[dom]["bytes"] / (us * 1e-6) / 1e9
         line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
@@ -599,6 +687,11 @@ def main():
                                "live_frac": round(v["bytes"] / (live[k][0] * 1e-6) / 1e9 / peak, 3) if k in live else None}
                            for k, v in kt.items()}
         line["hot_path_us_per_step"] = round(sum(v["us"] * v["per_step"] for v in kt.values()), 1)
+        if world == 1:
+            try:
+                line["extra_kernels"] = extra_kernel_rows(args, torch, peak)
+            except Exception as exc:
+                line["extra_kernels"] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
         line["hot_path_live_us_per_step"] = round(sum(t * n for t, n in live.values()), 1)
 
     # ---- informational: the same step under torch's DEFAULT conv math (TF32 tensor cores for cuDNN convolutions) ----

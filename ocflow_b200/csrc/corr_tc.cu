@@ -14,9 +14,9 @@
 // (measured against the fp64 oracle: 1e-6 relative, the FMA kernel has 1e-7; the bar is 1e-4).
 //
 // Roles in the 288-thread CTA (one CTA per SM, persistent over tiles):
-//   warps 4-7  producers   global (LDG.128, zero fill outside the image / past the last channel) -> split -> shared memory
-//                          in the UMMA MN-major no-swizzle canonical layout (16-byte chunks of 4 pixels, K stride 16 B, chunk
-//                          stride 128 B); optional feature normalisation (x - mean) * inv_std folded in (normalize_features,
+//   warps 4-7  producers   global (LDG.128, zero fill outside the image / past the last channel; loads run 2 stages ahead in
+//                          registers) -> split -> 4x4 register transpose -> shared memory in the UMMA K-major no-swizzle
+//                          canonical layout (16-byte chunks = 4 channels of one pixel); optional feature normalisation (x - mean) * inv_std folded in (normalize_features,
 //                          correlation_layer.py:42-82: zero padding stays zero AFTER normalisation, as in the reference)
 //   warp 8     MMA issuer  one thread: 6 x tcgen05.mma (M128 N192 K8) per 8-channel stage, tcgen05.commit -> mbarriers
 //   warps 0-3  epilogue    tcgen05.ld (TMEM lane = pixel) -> band selection by ADDRESS (the register index of a column is
@@ -35,10 +35,14 @@ constexpr int HROWS = TH + 2 * D;          // 24 halo rows
 constexpr int NHALF = HROWS * 8;           // 192 accumulator columns per x-half of the halo (n = half * 192 + row * 8 + x % 8)
 constexpr int KC = 8;                      // channels per stage = K of one kind::tf32 MMA
 constexpr int STAGES = 4;
-constexpr int A_BYTES = TH * TW * KC * 4;  // 4096
-constexpr int B_BYTES = 2 * NHALF * KC * 4;  // 12288
+// K-major no-swizzle canonical layout (pinned by tools/tc_probe.cu): element (mn, k) at (mn / 8) * SBO + (k / 4) * LBO + (mn % 8) * 16
+// + (k % 4) * 4 bytes -- core matrices of 8 rows x 16 B.  LBO / SBO carry 16 B of padding so that the producers' 128-bit
+// stores are bank-conflict free (slot index mod 8 = 2 * row + channel group + 4 * chunk).
+constexpr int LBO = 144, SBO = 288;
+constexpr int A_BYTES = TH * SBO;              // 16 row groups (one tile row of 8 pixels each): 4608
+constexpr int B_BYTES = 2 * HROWS * SBO;       // 2 x-halves x 24 halo rows: 13824
 constexpr int OFF_ALO = A_BYTES, OFF_BHI = 2 * A_BYTES, OFF_BLO = 2 * A_BYTES + B_BYTES;
-constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);  // 32768
+constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);  // 36864
 constexpr int PS = 132;                    // floats per staged output plane (128 pixels + 4: 16-byte aligned rows, <= 2-way bank conflicts)
 constexpr int STAGING_BYTES = NP * PS * 4;
 constexpr int THREADS = 288;
@@ -71,7 +75,8 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(unsigned long long* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// shared-memory matrix descriptor, no swizzle: start address, leading (K-group) byte offset, stride (16-byte chunk) byte offset
+// shared-memory matrix descriptor, K-major, no swizzle: start address, leading byte offset (between the two 4-channel core
+// matrices of one K = 8 step), stride byte offset (between groups of 8 rows)
 __device__ __forceinline__ unsigned long long umma_desc(unsigned addr, unsigned lbo_bytes, unsigned sbo_bytes) {
   return (unsigned long long)((addr >> 4) & 0x3FFF) | ((unsigned long long)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((unsigned long long)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
@@ -94,11 +99,9 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&r)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ float tf32_rna(float x) {
-  unsigned r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+// round to the nearest tf32 (10 mantissa bits) with integer ops at full rate; the tensor core TRUNCATES fp32 operands to tf32
+// (measured, tools/tc_probe.cu), so the rounding has to happen here for the hi / lo split to be exact
+__device__ __forceinline__ float tf32_round(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ void sts128(unsigned addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -149,99 +152,145 @@ corr_fwd_tc_kernel(const float* __restrict__ f1, const float* __restrict__ f2, f
 
   if (warp >= 4 && warp < 8) {
     // =========================== producers ===========================
+    // A unit of work = 4 channels x 4 adjacent pixels (4 x LDG.128 along x), transposed in registers into 4 x STS.128 of
+    // [4 channels] per pixel: the K-major canonical layout wants the channels (K) of one pixel contiguous.  256 units per stage
+    // (64 for the f1 tile, 192 for the f2 halo), two per thread.  Lane bits 0-2 = (channel group, chunk parity, row parity):
+    // with LBO = 144 B and SBO = 288 B these 8 lanes hit 8 distinct 16-byte bank groups (conflict-free STS.128).
     const int p = tid - 128;
-    const int k = p & 7;                         // channel within the stage
-    const int ja = (p >> 3) & 1, rowa = p >> 4;  // A unit i (0,1): pixel row rowa + 8 i, 4-pixel chunk ja
-    const int jb = (p >> 3) & 3, rowb = p >> 5;  // B unit i (0..5): halo row rowb + 4 i, chunk jb (x-half jb >> 1)
-    const unsigned offa = (unsigned)((rowa * 2 + ja) * 128 + k * 16);
-    const unsigned offb = (unsigned)(((jb >> 1) * (NHALF / 4) + rowb * 2 + (jb & 1)) * 128 + k * 16);
+    const bool u0_is_a = p < 64;
+    // unit 0: f1 unit p (p < 64) or f2 unit p - 64 ; unit 1: f2 unit p + 64
+    int kg[2], row[2], jx[2];
+    bool isa[2];
+    {
+      const int ua = p, ub0 = p - 64, ub1 = p + 64;
+      isa[0] = u0_is_a; isa[1] = false;
+      kg[0] = p & 1; kg[1] = p & 1;
+      if (u0_is_a) { jx[0] = (ua >> 1) & 1; row[0] = ((ua >> 3) << 1) | ((ua >> 2) & 1); }
+      else { jx[0] = (((ub0 >> 3) & 1) << 1) | ((ub0 >> 1) & 1); row[0] = ((ub0 >> 4) << 1) | ((ub0 >> 2) & 1); }
+      jx[1] = (((ub1 >> 3) & 1) << 1) | ((ub1 >> 1) & 1); row[1] = ((ub1 >> 4) << 1) | ((ub1 >> 2) & 1);
+    }
+    // shared-memory offset of pixel 0 of the unit (hi plane): row-group * SBO + channel-group * LBO + (x % 8) * 16
+    unsigned soff[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (isa[i]) soff[i] = (unsigned)(row[i] * SBO + kg[i] * LBO + (4 * jx[i]) * 16);
+      else soff[i] = (unsigned)(OFF_BHI + ((jx[i] >> 1) * HROWS + row[i]) * SBO + kg[i] * LBO + (4 * (jx[i] & 1)) * 16);
+    }
     float nmean = 0.f, ninv = 1.f;
     if (norm != nullptr) { nmean = __ldg(norm); ninv = __ldg(norm + 1); }
-    int n = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const TileCoord tc = tile_coord(tile, tiles_x, tiles_y);
-      const float* f1b = f1 + (size_t)tc.b * C * HW;
-      const float* f2b = f2 + (size_t)tc.b * C * HW;
-      const int xa = tc.x0 + 4 * ja, xb = tc.x0 - D + 4 * jb;
-      for (int s = 0; s < nst; ++s, ++n) {
-        const int slot = n % STAGES;
-        if (n >= STAGES) mbar_wait(&empty_bar[slot], ((n / STAGES) - 1) & 1);
-        const int c = s * KC + k;
-        const bool cok = c < C;
-        float4 v[8];
-        unsigned okm[8];   // per-element validity (bit e) of the 8 units
+    const int ntl = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total = ntl * nst;
+
+    // global loads of stage n into registers (no dependence on the ring: they run PF stages ahead of the stores)
+    auto load_stage = [&](int n, float4 (&v)[8], unsigned& okm) {
+      const int it = n / nst, s = n - it * nst;
+      const TileCoord tc = tile_coord((int)blockIdx.x + it * (int)gridDim.x, tiles_x, tiles_y);
+      okm = 0u;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const bool isa = i < 2;
-          const int y = isa ? tc.y0 + rowa + 8 * i : tc.y0 - D + rowb + 4 * (i - 2);
-          const int x = isa ? xa : xb;
-          const float* src = (isa ? f1b : f2b) + ((size_t)c * H + y) * W + x;
-          const bool rok = cok && y >= 0 && y < H;
-          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (VEC) {
-            const bool ok = rok && x >= 0 && x < W;
-            okm[i] = ok ? 0xFu : 0u;
-            if (ok) v[i] = __ldg(reinterpret_cast<const float4*>(src));
-          } else {
-            unsigned m = 0u;
-            if (rok) {
-              if (x >= 0 && x < W) { v[i].x = __ldg(src); m |= 1u; }
-              if (x + 1 >= 0 && x + 1 < W) { v[i].y = __ldg(src + 1); m |= 2u; }
-              if (x + 2 >= 0 && x + 2 < W) { v[i].z = __ldg(src + 2); m |= 4u; }
-              if (x + 3 >= 0 && x + 3 < W) { v[i].w = __ldg(src + 3); m |= 8u; }
+      for (int i = 0; i < 2; ++i) {
+        const int y = isa[i] ? tc.y0 + row[i] : tc.y0 - D + row[i];
+        const int x = isa[i] ? tc.x0 + 4 * jx[i] : tc.x0 - D + 4 * jx[i];
+        const float* base = (isa[i] ? f1 : f2) + (size_t)tc.b * C * HW;
+        const bool rok = y >= 0 && y < H;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c = s * KC + kg[i] * 4 + q;
+          const float* src = base + ((size_t)c * H + y) * W + x;
+          float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+          unsigned m = 0u;
+          if (rok && c < C) {
+            if (VEC) {
+              if (x >= 0 && x < W) { r = __ldg(reinterpret_cast<const float4*>(src)); m = 0xFu; }
+            } else {
+              if (x >= 0 && x < W) { r.x = __ldg(src); m |= 1u; }
+              if (x + 1 >= 0 && x + 1 < W) { r.y = __ldg(src + 1); m |= 2u; }
+              if (x + 2 >= 0 && x + 2 < W) { r.z = __ldg(src + 2); m |= 4u; }
+              if (x + 3 >= 0 && x + 3 < W) { r.w = __ldg(src + 3); m |= 8u; }
             }
-            okm[i] = m;
           }
+          v[i * 4 + q] = r;
+          okm |= m << ((i * 4 + q) * 4);
         }
-        const unsigned sbase = smem_u32(smem) + (unsigned)slot * STAGE_BYTES;
+      }
+    };
+    // normalise, split into tf32 hi / lo, transpose 4 channels x 4 pixels and store stage n
+    auto store_stage = [&](int n, const float4 (&v)[8], unsigned okm) {
+      const int slot = n % STAGES;
+      if (n >= STAGES) mbar_wait(&empty_bar[slot], ((n / STAGES) - 1) & 1);
+      const unsigned sbase = smem_u32(smem) + (unsigned)slot * STAGE_BYTES;
+      const int it = n / nst, s = n - it * nst;
+      const TileCoord tc = tile_coord((int)blockIdx.x + it * (int)gridDim.x, tiles_x, tiles_y);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const bool isa = i < 2;
-          float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-          if (norm != nullptr) {
+      for (int i = 0; i < 2; ++i) {
+        float e[4][4];   // [channel q][pixel]
 #pragma unroll
-            for (int q = 0; q < 4; ++q) e[q] = (okm[i] >> q) & 1u ? (e[q] - nmean) * ninv : 0.f;
-            if (isa && f1n_out != nullptr && okm[i]) {
-              // the normalised first feature map is an output of the level (it is concatenated into the decoder input,
-              // cost_volume_flow_net.py:190): every A element is loaded exactly once per launch, so it is written from here
-              const int y = tc.y0 + rowa + 8 * i;
-              float* dst = f1n_out + (size_t)tc.b * (f1n_bstride ? (size_t)f1n_bstride : (size_t)C * HW) + ((size_t)c * H + y) * W + xa;
-              if (VEC) *reinterpret_cast<float4*>(dst) = make_float4(e[0], e[1], e[2], e[3]);
+        for (int q = 0; q < 4; ++q) {
+          const float4 r = v[i * 4 + q];
+          e[q][0] = r.x; e[q][1] = r.y; e[q][2] = r.z; e[q][3] = r.w;
+        }
+        if (norm != nullptr) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const unsigned m = (okm >> ((i * 4 + q) * 4)) & 0xFu;
+#pragma unroll
+            for (int px = 0; px < 4; ++px) e[q][px] = (m >> px) & 1u ? (e[q][px] - nmean) * ninv : 0.f;
+            // the normalised feature maps are outputs of the level: c1n is concatenated into the decoder input
+            // (cost_volume_flow_net.py:190), c2n is kept for the backward.  Every f1 element and the interior of the f2 halo
+            // box (rows 4..19, chunks 1 and 2 = this tile's own 16 x 8 pixels) are loaded by exactly one tile.
+            float* dst = nullptr;
+            const int c = s * KC + kg[i] * 4 + q;
+            if (isa[i]) {
+              if (f1n_out != nullptr)
+                dst = f1n_out + (size_t)tc.b * (f1n_bstride ? (size_t)f1n_bstride : (size_t)C * HW) + ((size_t)c * H + tc.y0 + row[i]) * W + tc.x0 + 4 * jx[i];
+            } else if (f2n_out != nullptr && (jx[i] == 1 || jx[i] == 2) && row[i] >= D && row[i] < D + TH) {
+              dst = f2n_out + (size_t)tc.b * C * HW + ((size_t)c * H + tc.y0 - D + row[i]) * W + tc.x0 - D + 4 * jx[i];
+            }
+            if (dst != nullptr && m) {
+              if (VEC) *reinterpret_cast<float4*>(dst) = make_float4(e[q][0], e[q][1], e[q][2], e[q][3]);
               else {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) if ((okm[i] >> q) & 1u) dst[q] = e[q];
-              }
-            }
-            if (!isa && f2n_out != nullptr && okm[i] && (jb == 1 || jb == 2)) {
-              // the normalised second feature map (needed by the backward): the interior of the halo box -- rows 4..19, chunks
-              // 1 and 2 -- is this tile's own 16 x 8 pixels, loaded by exactly one tile
-              const int r = rowb + 4 * (i - 2);
-              if (r >= D && r < D + TH) {
-                float* dst = f2n_out + (size_t)tc.b * C * HW + ((size_t)c * H + (tc.y0 - D + r)) * W + xb;
-                if (VEC) *reinterpret_cast<float4*>(dst) = make_float4(e[0], e[1], e[2], e[3]);
-                else {
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) if ((okm[i] >> q) & 1u) dst[q] = e[q];
-                }
+                for (int px = 0; px < 4; ++px) if ((m >> px) & 1u) dst[px] = e[q][px];
               }
             }
           }
+        }
+        const unsigned a = sbase + soff[i];
+        const unsigned lo_off = isa[i] ? (unsigned)A_BYTES : (unsigned)B_BYTES;
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
           float hi[4], lo[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) { hi[q] = tf32_rna(e[q]); lo[q] = tf32_rna(e[q] - hi[q]); }
-          const unsigned a = sbase + (isa ? offa + (unsigned)(i * 16 * 128) : OFF_BHI + offb + (unsigned)((i - 2) * 8 * 128));
-          sts128(a, hi[0], hi[1], hi[2], hi[3]);
-          sts128(a + (isa ? A_BYTES : B_BYTES), lo[0], lo[1], lo[2], lo[3]);
+          for (int q = 0; q < 4; ++q) { hi[q] = tf32_round(e[q][px]); lo[q] = tf32_round(e[q][px] - hi[q]); }
+          sts128(a + px * 16, hi[0], hi[1], hi[2], hi[3]);
+          sts128(a + px * 16 + lo_off, lo[0], lo[1], lo[2], lo[3]);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core (async proxy)
-        mbar_arrive(&full_bar[slot]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core (async proxy)
+      mbar_arrive(&full_bar[slot]);
+    };
+
+    // software pipeline: the loads of stage n + 2 are in flight while stage n is converted and stored (3 register buffers)
+    float4 v0[8], v1[8], v2[8];
+    unsigned m0 = 0u, m1 = 0u, m2 = 0u;
+    if (total > 0) load_stage(0, v0, m0);
+    if (total > 1) load_stage(1, v1, m1);
+    for (int n = 0; n < total; n += 3) {
+      if (n + 2 < total) load_stage(n + 2, v2, m2);
+      store_stage(n, v0, m0);
+      if (n + 1 < total) {
+        if (n + 3 < total) load_stage(n + 3, v0, m0);
+        store_stage(n + 1, v1, m1);
+      }
+      if (n + 2 < total) {
+        if (n + 4 < total) load_stage(n + 4, v1, m1);
+        store_stage(n + 2, v2, m2);
       }
     }
   } else if (warp == 8) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      // instruction descriptor: D fp32, A/B tf32, both MN-major, N = 192, M = 128
-      constexpr unsigned IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(NHALF >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+      // instruction descriptor: D fp32, A/B tf32, both K-major, N = 192, M = 128
+      constexpr unsigned IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(NHALF >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
       int n = 0, t = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
         for (int s = 0; s < nst; ++s, ++n) {
@@ -249,15 +298,15 @@ corr_fwd_tc_kernel(const float* __restrict__ f1, const float* __restrict__ f2, f
           mbar_wait(&full_bar[slot], (n / STAGES) & 1);
           tc_fence_after();
           const unsigned sbase = smem_u32(smem) + (unsigned)slot * STAGE_BYTES;
-          const unsigned long long ahi = umma_desc(sbase, STAGE_BYTES, 128), alo = umma_desc(sbase + OFF_ALO, STAGE_BYTES, 128);
+          const unsigned long long ahi = umma_desc(sbase, LBO, SBO), alo = umma_desc(sbase + OFF_ALO, LBO, SBO);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             if (s == 0) {   // the epilogue must have drained this half of the previous tile's accumulator
               mbar_wait(&tmem_empty_bar[h], (t & 1) ^ 1);
               tc_fence_after();
             }
-            const unsigned long long bhi = umma_desc(sbase + OFF_BHI + h * (B_BYTES / 2), STAGE_BYTES, 128);
-            const unsigned long long blo = umma_desc(sbase + OFF_BLO + h * (B_BYTES / 2), STAGE_BYTES, 128);
+            const unsigned long long bhi = umma_desc(sbase + OFF_BHI + h * (B_BYTES / 2), LBO, SBO);
+            const unsigned long long blo = umma_desc(sbase + OFF_BLO + h * (B_BYTES / 2), LBO, SBO);
             const unsigned d = tb + (unsigned)(h * NHALF);
             umma_tf32(d, ahi, bhi, IDESC, s > 0 ? 1u : 0u);
             umma_tf32(d, ahi, blo, IDESC, 1u);
