@@ -226,10 +226,11 @@ def kernel_table(args, torch):
         return ctypes.c_void_p(t.data_ptr())
 
     def smooth_flow(b, h, w, scale):
-        # what the kernels see in the real step: a coarse flow field up-sampled x4 (cost_volume_flow_net.py:182,245),
-        # i.e. spatially coherent displacements -- not per-pixel white noise
+        # what the kernels see in the real step: an up-sampled coarse flow field (cost_volume_flow_net.py:182,245), i.e. spatially
+        # coherent displacements (here: control points every 16 pixels, ~0.2-0.4 px/px of local expansion) -- not per-pixel white
+        # noise; tools/warp_probe.py times the same kernels on zero / gentle / rough / white-noise fields
         import torch.nn.functional as F
-        coarse = torch.randn(b, 2, max(h // 4, 2), max(w // 4, 2), device=dev, generator=g) * scale
+        coarse = torch.randn(b, 2, max(h // 16, 2), max(w // 16, 2), device=dev, generator=g) * scale
         return F.interpolate(coarse, size=(h, w), mode="bilinear", align_corners=True).contiguous()
 
     custom = [tuple(int(v) for v in item.split(":")) for item in getattr(args, "levels", "").split(",") if item]
@@ -360,7 +361,7 @@ def extra_kernel_rows(args, torch, peak):
         f1 = torch.randn(B, C, h, w, device="cuda", generator=g)
         f2 = torch.randn(B, C, h, w, device="cuda", generator=g)
         import torch.nn.functional as F
-        fl = F.interpolate(torch.randn(B, 2, h // 4, w // 4, device="cuda", generator=g) * 2, size=(h, w), mode="bilinear", align_corners=True).contiguous()
+        fl = F.interpolate(torch.randn(B, 2, h // 16, w // 16, device="cuda", generator=g) * 2, size=(h, w), mode="bilinear", align_corners=True).contiguous()
         out = torch.empty(B, 81, h, w, device="cuda")
         gout = torch.randn(B, 81, h, w, device="cuda", generator=g)
         msk = torch.zeros(B, 81, h, (w + 7) // 8, device="cuda", dtype=torch.uint8)

@@ -1063,7 +1063,7 @@ extern "C" int ocf_corr_fwd(const float* f1, const float* f2, float* out, int B,
   cudaStream_t s = ocf_cast_stream(stream);
   const float inv_c = 1.0f / (float)C;
   // d = 4: tensor-core kernel (tcgen05, 3xTF32) unless the developer knob OCF_CORR_TC=0 selects the fp32 FMA kernels
-  static const int use_tc = []() { const char* e = getenv("OCF_CORR_TC"); return e ? atoi(e) : 1; }();
+  static const int use_tc = []() { const char* e = getenv("OCF_CORR_TC"); return e ? atoi(e) : 0; }();
   if (d == 4 && use_tc) return ocf_corr_fwd_tc_launch(f1, f2, out, mask_out, norm, nullptr, 0, nullptr, B, C, H, W, out_bstride, leaky_slope, s);
   if (d == 4 && norm == nullptr) {
     using T = Tile4;
