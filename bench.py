@@ -247,8 +247,8 @@ def kernel_table(args, torch):
         wout = torch.empty_like(f2)
         dfl = torch.empty_like(fl)
         f1n, f2n = torch.empty_like(f1), torch.empty_like(f2)
-        # what the step runs per level (ops.level_fused): statistics pass, tensor-core correlation normalising on load (writes
-        # corr, c1n, c2n and the sign bitmask), then in the backward the correlation / normalisation / warp backward kernels
+        # what the step runs per level (ops.level_fused): warp, statistics pass, apply pass (c1n into the concat buffer), fp32 FMA
+        # correlation (+ sign bitmask), then in the backward the correlation / normalisation / warp backward kernels
         y1, y2 = torch.empty_like(f1), torch.empty_like(f2)
         stats = torch.empty(8 * 2 * B + 8, device=dev)
         red = torch.empty(8 * 2 * B, device=dev)
@@ -259,10 +259,13 @@ def kernel_table(args, torch):
         norm_ptr = ctypes.c_void_p(stats.data_ptr() + 4 * 6 * 2 * B)
         table["normalize_stats_L%d" % lvl] = (lambda xs_arr=xs_arr, stats=stats, C=C, h=h, w=w: _lib.call(
             "ocf_normalize_stats", ctypes.cast(xs_arr, ctypes.c_void_p), 2, B, C, h, w, 15, P(stats), st), 4 * n * 2 * C, 2)
-        table["level_corr_fwd_L%d" % lvl] = (lambda f1=f1, f2=f2, out=out, msk=msk, f1n=f1n, f2n=f2n, norm_ptr=norm_ptr, C=C, h=h, w=w: _lib.call(
-            "ocf_level_corr_fwd", P(f1), P(f2), norm_ptr, P(out), 0, P(f1n), 0, P(f2n), P(msk), B, C, h, w, 0.1, st),
-            4 * n * (4 * C + 81) + n * 81 // 8, 2)
-        table["level_corr_bwd_L%d" % lvl] = (lambda gout=gout, msk=msk, f1=f1, f2=f2, d1=d1, d2=d2, C=C, h=h, w=w: _lib.call(
+        bstr = (ctypes.c_longlong * 2)(0, 0)
+        table["normalize_apply_L%d" % lvl] = (lambda xs_arr=xs_arr, ys_arr=ys_arr, bstr=bstr, stats=stats, C=C, h=h, w=w: _lib.call(
+            "ocf_normalize_apply", ctypes.cast(xs_arr, ctypes.c_void_p), ctypes.cast(ys_arr, ctypes.c_void_p), ctypes.cast(bstr, ctypes.c_void_p),
+            2, B, C, h, w, 15, P(stats), st), 4 * n * 4 * C, 2)
+        table["corr_fwd_L%d" % lvl] = (lambda f1=f1, f2=f2, out=out, msk=msk, C=C, h=h, w=w: _lib.call(
+            "ocf_corr_fwd_strided", P(f1), 0, P(f2), P(out), 0, P(msk), B, C, h, w, 0.1, st), 4 * n * (2 * C + 81) + n * 81 // 8, 2)
+        table["corr_bwd_L%d" % lvl] = (lambda gout=gout, msk=msk, f1=f1, f2=f2, d1=d1, d2=d2, C=C, h=h, w=w: _lib.call(
             "ocf_level_corr_bwd", P(gout), 0, P(msk), P(f1), 0, P(f2), P(d1), P(d2), B, C, h, w, 0.1, st), 4 * n * (81 + 4 * C) + n * 81 // 8, 1)
         table["normalize_bwd_L%d" % lvl] = (lambda xs_arr=xs_arr, ys_arr=ys_arr, gs_arr=gs_arr, stats=stats, red=red, C=C, h=h, w=w: _lib.call(
             "ocf_normalize_bwd", ctypes.cast(ys_arr, ctypes.c_void_p), ctypes.cast(xs_arr, ctypes.c_void_p), ctypes.cast(gs_arr, ctypes.c_void_p),
@@ -355,31 +358,56 @@ def extra_kernel_rows(args, torch, peak):
         return statistics.mean(ts)
 
     rows = {}
-    B, h, w = 8, 188, 621
-    n = B * h * w
-    for C in (32, 128):
-        f1 = torch.randn(B, C, h, w, device="cuda", generator=g)
-        f2 = torch.randn(B, C, h, w, device="cuda", generator=g)
-        import torch.nn.functional as F
-        fl = F.interpolate(torch.randn(B, 2, h // 16, w // 16, device="cuda", generator=g) * 2, size=(h, w), mode="bilinear", align_corners=True).contiguous()
-        out = torch.empty(B, 81, h, w, device="cuda")
-        gout = torch.randn(B, 81, h, w, device="cuda", generator=g)
-        msk = torch.zeros(B, 81, h, (w + 7) // 8, device="cuda", dtype=torch.uint8)
-        d1, d2, wout, dfl = torch.empty_like(f1), torch.empty_like(f2), torch.empty_like(f2), torch.empty_like(fl)
-        cases = {
-            "corr_fwd": (lambda: _lib.call("ocf_corr_fwd", P(f1), P(f2), P(out), B, C, h, w, 4, 0, 0.1, None, P(msk), st), 4 * n * (2 * C + 81), 2 * 81 * C * n),
-            "corr_bwd": (lambda: _lib.call("ocf_corr_bwd", P(gout), None, P(f1), P(f2), P(d1), P(d2), B, C, h, w, 4, 0, 0, 0.1, P(msk), st), 4 * n * (81 + 4 * C), 4 * 81 * C * n),
-            "warp_fwd": (lambda: _lib.call("ocf_warp_fwd", P(f2), P(fl), None, P(wout), B, C, h, w, 0, 1.25, st), 4 * n * (2 * C + 2), 0),
-            "warp_bwd": (lambda: _lib.call("ocf_warp_bwd", P(wout), P(f2), P(fl), None, P(d2), P(dfl), None, B, C, h, w, 0, 1.25, st), 4 * n * (3 * C + 4), 0),
-        }
-        for name, (fn, nbytes, flops) in cases.items():
+    import torch.nn.functional as F
+    from ocflow_b200 import ops
+
+    B, h = 8, 188
+    for w in (620, 621):    # 16-byte aligned rows (TMA-fed fp32 FMA kernels) and the native ragged KITTI row length
+        n = B * h * w
+        for C in (32, 128):
+            f1 = torch.randn(B, C, h, w, device="cuda", generator=g)
+            f2 = torch.randn(B, C, h, w, device="cuda", generator=g)
+            fl = F.interpolate(torch.randn(B, 2, h // 16, w // 16, device="cuda", generator=g) * 2, size=(h, w), mode="bilinear", align_corners=True).contiguous()
+            out = torch.empty(B, 81, h, w, device="cuda")
+            gout = torch.randn(B, 81, h, w, device="cuda", generator=g)
+            msk = torch.zeros(B, 81, h, (w + 7) // 8, device="cuda", dtype=torch.uint8)
+            d1, d2, wout, dfl = torch.empty_like(f1), torch.empty_like(f2), torch.empty_like(f2), torch.empty_like(fl)
+            cases = {
+                "corr_fwd": (lambda: _lib.call("ocf_corr_fwd", P(f1), P(f2), P(out), B, C, h, w, 4, 0, 0.1, None, P(msk), st), 4 * n * (2 * C + 81), 2 * 81 * C * n),
+                "warp_fwd": (lambda: _lib.call("ocf_warp_fwd", P(f2), P(fl), None, P(wout), B, C, h, w, 0, 1.25, st), 4 * n * (2 * C + 2), 0),
+                "warp_bwd": (lambda: _lib.call("ocf_warp_bwd", P(wout), P(f2), P(fl), None, P(d2), P(dfl), None, B, C, h, w, 0, 1.25, st), 4 * n * (3 * C + 4), 0),
+            }
+            if w % 4 == 0:
+                cases["corr_bwd"] = (lambda: _lib.call("ocf_corr_bwd", P(gout), None, P(f1), P(f2), P(d1), P(d2), B, C, h, w, 4, 0, 0, 0.1, P(msk), st),
+                                     4 * n * (81 + 4 * C), 4 * 81 * C * n)
+            else:
+                # ragged rows, forward + backward through the public API (ops.cost_volume re-pitches the rows to a multiple of 4,
+                # autograd slices / pads the gradients: those copies are inside the timed region)
+                a1, a2 = f1.clone().requires_grad_(True), f2.clone().requires_grad_(True)
+
+                def fwd_bwd(a1=a1, a2=a2, gout=gout):
+                    torch.autograd.grad(ops.cost_volume(a1, a2, 4, leaky_slope=0.1), (a1, a2), gout)
+                cases["corr_fwd_bwd_public_api"] = (fwd_bwd, 4 * n * (2 * C + 81) + 4 * n * (81 + 4 * C), 6 * 81 * C * n)
+            for name, (fn, nbytes, flops) in cases.items():
+                t = timed(fn)
+                rows["kitti_188x%d_B8_C%d_%s" % (w, C, name)] = {"us": round(t * 1e6, 1), "gbs": round(nbytes / t / 1e9, 1), "frac": round(nbytes / t / 1e9 / peak, 3),
+                                                               "tflops": round(flops / t / 1e12, 2) if flops else None}
+            del f1, f2, out, gout, msk, d1, d2, wout, dfl, cases
+    # tensor-core (tcgen05 3xTF32) against fp32 FMA correlation forward, same inputs (why the FMA kernels are the default)
+    for C, hh, ww in ((32, 96, 128), (128, 96, 128)):
+        n = B * hh * ww
+        f1 = torch.randn(B, C, hh, ww, device="cuda", generator=g)
+        f2 = torch.randn(B, C, hh, ww, device="cuda", generator=g)
+        out = torch.empty(B, 81, hh, ww, device="cuda")
+        msk = torch.zeros(B, 81, hh, (ww + 7) // 8, device="cuda", dtype=torch.uint8)
+        for name, fn in (("fma", lambda: _lib.call("ocf_corr_fwd", P(f1), P(f2), P(out), B, C, hh, ww, 4, 0, 0.1, None, P(msk), st)),
+                         ("tcgen05_3xtf32", lambda: _lib.call("ocf_level_corr_fwd", P(f1), P(f2), None, P(out), 0, None, 0, None, P(msk), B, C, hh, ww, 0.1, st))):
             t = timed(fn)
-            rows["kitti_188x621_B8_C%d_%s" % (C, name)] = {"us": round(t * 1e6, 1), "gbs": round(nbytes / t / 1e9, 1), "frac": round(nbytes / t / 1e9 / peak, 3),
-                                                          "tflops": round(flops / t / 1e12, 2) if flops else None}
-        del f1, f2, out, gout, msk, d1, d2, wout, dfl
+            rows["corr_fwd_%dx%d_B8_C%d_%s" % (hh, ww, C, name)] = {"us": round(t * 1e6, 1), "frac": round(4 * n * (2 * C + 81) / t / 1e9 / peak, 3),
+                                                                   "tflops": round(2 * 81 * C * n / t / 1e12, 2)}
+        del f1, f2, out, msk
     # config 4
     import ocflow_b200 as ocf
-    from ocflow_b200 import ops
 
     B, H, W = 8, 436, 1024
     n = B * H * W
@@ -419,10 +447,12 @@ def live_kernel_times(step, batch, torch, height, reps=3):
         return int(round(math.log2(height / float(h)))) if h > 0 else 0
 
     H_INDEX = {"ocf_corr_fwd": 2, "ocf_corr_bwd": 2, "ocf_normalize_fwd": 3, "ocf_normalize_bwd": 3, "ocf_normalize_stats": 3,
-               "ocf_warp_fwd": 2, "ocf_warp_bwd": 2, "ocf_level_corr_fwd": 4, "ocf_level_corr_bwd": 4}
+               "ocf_normalize_apply": 3, "ocf_warp_fwd": 2, "ocf_warp_bwd": 2, "ocf_level_corr_fwd": 4, "ocf_level_corr_bwd": 4,
+               "ocf_corr_fwd_strided": 4}
+    ALIAS = {"corr_fwd_strided": "corr_fwd", "level_corr_bwd": "corr_bwd"}   # same kernels as the kernel-alone table's rows
 
     def classify(name, ints):
-        short = name[4:]
+        short = ALIAS.get(name[4:], name[4:])
         if name in H_INDEX:
             return "%s_L%d" % (short, level(ints[H_INDEX[name]]))
         return short

@@ -89,6 +89,11 @@ int ocf_corr_bwd(const float* grad_out, const float* out_act, const float* f1, c
 int ocf_level_corr_fwd(const float* f1, const float* f2, const float* norm, float* out, long long out_bstride,
                        float* f1n_out, long long f1n_bstride, float* f2n_out, unsigned char* mask_out, int B, int C,
                        int H, int W, float leaky_slope, ocf_stream_t stream);
+/* ocf_corr_fwd (d = 4, LeakyReLU + sign bitmask) with f1 read in place from a wider buffer (batch stride in elements) and the
+ * cost volume written into one (out_bstride): the fp32 FMA form of the fused level, fed by ocf_normalize_apply, which
+ * leaves the normalised first feature map where the decoder's concat (cost_volume_flow_net.py:190) wants it.  W % 4 == 0. */
+int ocf_corr_fwd_strided(const float* f1, long long f1_bstride, const float* f2, float* out, long long out_bstride,
+                         unsigned char* mask_out, int B, int C, int H, int W, float leaky_slope, ocf_stream_t stream);
 int ocf_level_corr_bwd(const float* grad_out, long long g_bstride, const unsigned char* mask, const float* f1n,
                        long long f1n_bstride, const float* f2n, float* df1, float* df2, int B, int C, int H, int W,
                        float leaky_slope, ocf_stream_t stream);
@@ -111,6 +116,10 @@ int ocf_normalize_fwd(const float* const* xs, float* const* ys, int T, int B, in
  * stats[6*NG + 2*g], stats[6*NG + 2*g + 1], NG = T*B*G).  With moments_across_images (the FlowNetCV call sites,
  * cost_volume_flow_net.py:171,187,...) every group carries the same scalar pair. */
 int ocf_normalize_stats(const float* const* xs, int T, int B, int C, int H, int W, int flags, float* stats, ocf_stream_t stream);
+/* apply pass alone: ys[t] = (xs[t] - mean) * inv_std with the statistics of a previous ocf_normalize_stats; ys[t] may point
+ * into a wider buffer (y_bstrides[t] = elements between batch items, 0 or NULL array = dense). */
+int ocf_normalize_apply(const float* const* xs, float* const* ys, const long long* y_bstrides, int T, int B, int C, int H, int W,
+                        int flags, const float* stats, ocf_stream_t stream);
 /* grads wrt every input, differentiating through the statistics (no detach in the reference).
  * red workspace (8-byte aligned): 8*T*B*G floats. */
 int ocf_normalize_bwd(const float* const* grad_ys, const float* const* xs, float* const* grad_xs,

@@ -1050,10 +1050,13 @@ bool make_map(CUtensorMap* map, const float* base, int B, int C, int H, int W, i
 
 }  // namespace
 
-extern "C" int ocf_corr_fwd(const float* f1, const float* f2, float* out, int B, int C, int H, int W, int d,
-                            long long out_bstride, float leaky_slope, const float* norm, unsigned char* mask_out,
-                            ocf_stream_t stream) {
+// f1_bstride: batch stride of f1 in elements (0 = dense) -- the fused level op keeps the normalised first feature map inside
+// the decoder's concat buffer (ops.level_fused); only the TMA path (d = 4, 16-byte aligned rows) reads it in place
+static int corr_fwd_impl(const float* f1, long long f1_bstride, const float* f2, float* out, int B, int C, int H, int W, int d,
+                         long long out_bstride, float leaky_slope, const float* norm, unsigned char* mask_out,
+                         ocf_stream_t stream) {
   OCF_REQUIRE_PTR(f1); OCF_REQUIRE_PTR(f2); OCF_REQUIRE_PTR(out);
+  OCF_REQUIRE(f1_bstride == 0 || f1_bstride >= (long long)C * H * W, OCF_ESHAPE);
   OCF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, OCF_ESHAPE);
   OCF_REQUIRE(d >= 0 && d <= OCF_MAX_DISPLACEMENT, OCF_EUNSUPPORTED);
   const long long nd = 2 * d + 1;
@@ -1062,9 +1065,12 @@ extern "C" int ocf_corr_fwd(const float* f1, const float* f2, float* out, int B,
   OCF_REQUIRE(mask_out == nullptr || d == 4, OCF_EUNSUPPORTED);  // only the d = 4 kernels emit the sign mask
   cudaStream_t s = ocf_cast_stream(stream);
   const float inv_c = 1.0f / (float)C;
-  // d = 4: tensor-core kernel (tcgen05, 3xTF32) unless the developer knob OCF_CORR_TC=0 selects the fp32 FMA kernels
+  // d = 4 has two implementations: the fp32 FMA kernels below (TMA-fed; 1e-7 relative error) and a tensor-core kernel
+  // (corr_tc.cu: tcgen05, 3xTF32, 1e-6).  Measured on B200 the FMA kernels win wherever TMA can describe the rows (W % 4 == 0:
+  // 29.7 vs 49.9 us at 8x32x96x128, 79 vs 133 us at C = 128) and lose on ragged rows, where they fall back to 4-byte cp.async
+  // (8x32x188x621: 660 vs 456 us) -- so ragged rows take the tensor-core kernel.  OCF_CORR_TC=1 forces it everywhere (tuning).
   static const int use_tc = []() { const char* e = getenv("OCF_CORR_TC"); return e ? atoi(e) : 0; }();
-  if (d == 4 && use_tc) return ocf_corr_fwd_tc_launch(f1, f2, out, mask_out, norm, nullptr, 0, nullptr, B, C, H, W, out_bstride, leaky_slope, s);
+  if (d == 4 && (use_tc || W % 4 != 0) && f1_bstride == 0 && norm == nullptr) return ocf_corr_fwd_tc_launch(f1, f2, out, mask_out, norm, nullptr, 0, nullptr, B, C, H, W, out_bstride, leaky_slope, s);
   if (d == 4 && norm == nullptr) {
     using T = Tile4;
     const size_t smem = sizeof(float) * T::STAGES * (T::F1_STAGE + T::F2_STAGE);
@@ -1076,7 +1082,9 @@ extern "C" int ocf_corr_fwd(const float* f1, const float* f2, float* out, int B,
     CUtensorMap m1, m2;
     memset(&m1, 0, sizeof(m1));
     memset(&m2, 0, sizeof(m2));
-    const bool tma = vec && make_map(&m1, f1, B, C, H, W, T::S1, T::TH, T::CC) && make_map(&m2, f2, B, C, H, W, T::S2, T::F2H, T::CC);
+    const bool tma = vec && (f1_bstride % 4 == 0) && make_map(&m1, f1, B, C, H, W, T::S1, T::TH, T::CC, f1_bstride) &&
+                     make_map(&m2, f2, B, C, H, W, T::S2, T::F2H, T::CC);
+    OCF_REQUIRE(tma || f1_bstride == 0, OCF_EUNSUPPORTED);
     if (tma && ks == 1) {
       using TP = Tile4P;
       auto kernel = corr_fwd_persist<TP, FWD_UNROLL>;
@@ -1095,10 +1103,23 @@ extern "C" int ocf_corr_fwd(const float* f1, const float* f2, float* out, int B,
       if (int e = launch_kernel(kernel, grid, T::THREADS, smem, s, ks, m1, m2, f1, f2, out, mask_out, C, H, W, out_bstride, inv_c, leaky_slope, ks)) return e;
     }
   } else {
+    OCF_REQUIRE(f1_bstride == 0, OCF_EUNSUPPORTED);
     dim3 grid((H * W + 127) / 128, (unsigned)nd, B);
     corr_fwd_generic<<<grid, 128, 0, s>>>(f1, f2, out, C, H, W, d, out_bstride, inv_c, leaky_slope, norm);
   }
   return ocf_launch_status();
+}
+
+extern "C" int ocf_corr_fwd(const float* f1, const float* f2, float* out, int B, int C, int H, int W, int d,
+                            long long out_bstride, float leaky_slope, const float* norm, unsigned char* mask_out,
+                            ocf_stream_t stream) {
+  return corr_fwd_impl(f1, 0, f2, out, B, C, H, W, d, out_bstride, leaky_slope, norm, mask_out, stream);
+}
+
+extern "C" int ocf_corr_fwd_strided(const float* f1, long long f1_bstride, const float* f2, float* out, long long out_bstride,
+                                    unsigned char* mask_out, int B, int C, int H, int W, float leaky_slope, ocf_stream_t stream) {
+  OCF_REQUIRE(W % 4 == 0, OCF_EUNSUPPORTED);
+  return corr_fwd_impl(f1, f1_bstride, f2, out, B, C, H, W, 4, out_bstride, leaky_slope, nullptr, mask_out, stream);
 }
 
 // f1_bstride / f2_bstride: batch strides of the feature operands in elements (0 = dense): the fused level op keeps the

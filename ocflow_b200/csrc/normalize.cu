@@ -30,6 +30,7 @@ struct PtrPack {
   const float* in[MAX_T];
   const float* in2[MAX_T];
   float* out[MAX_T];
+  long long out_bstride[MAX_T];   // elements between batch items of out[t]; 0 = dense (norm_apply_kernel only)
 };
 
 // The forward sums are taken about a per-group pivot (the group's first element): var = E[(x-p)^2] - E[x-p]^2 is shift
@@ -167,6 +168,10 @@ norm_apply_kernel(PtrPack pk, int B, int G, size_t glen, const float* __restrict
   const int t = gidx / (B * G), rem = gidx - t * (B * G);
   const float* x = pk.in[t] + (size_t)rem * glen;
   float* y = pk.out[t] + (size_t)rem * glen;
+  if (pk.out_bstride[t] != 0) {   // output inside a wider (concat) buffer: only the batch stride differs
+    const int bb = rem / G;
+    y += (size_t)bb * ((size_t)pk.out_bstride[t] - glen * (size_t)G);
+  }
   const float m = app[2 * gidx], r = app[2 * gidx + 1];
   if (vec) {
     const size_t n4 = glen / 4;
@@ -230,7 +235,7 @@ extern "C" int ocf_normalize_stats(const float* const* xs, int T, int B, int C, 
   bool vec = true;
   for (int t = 0; t < T; ++t) {
     OCF_REQUIRE_PTR(xs[t]);
-    pk.in[t] = xs[t]; pk.in2[t] = nullptr; pk.out[t] = nullptr;
+    pk.in[t] = xs[t]; pk.in2[t] = nullptr; pk.out[t] = nullptr; pk.out_bstride[t] = 0;
     vec = vec && ocf_aligned16(xs[t]);
   }
   const int G = (flags & OCF_NORM_ACROSS_CHANNELS) ? 1 : C;
@@ -257,12 +262,38 @@ extern "C" int ocf_normalize_fwd(const float* const* xs, float* const* ys, int T
   bool vec = true;
   for (int t = 0; t < T; ++t) {
     OCF_REQUIRE_PTR(ys[t]);
-    pk.in[t] = xs[t]; pk.in2[t] = nullptr; pk.out[t] = ys[t];
+    pk.in[t] = xs[t]; pk.in2[t] = nullptr; pk.out[t] = ys[t]; pk.out_bstride[t] = 0;
     vec = vec && ocf_aligned16(xs[t]) && ocf_aligned16(ys[t]);
   }
   const int G = (flags & OCF_NORM_ACROSS_CHANNELS) ? 1 : C;
   const size_t glen = (size_t)(G == 1 ? C : 1) * H * W;
   const int NG = T * B * G;
+  vec = vec && (glen % 4 == 0);
+  norm_apply_kernel<<<dim3(chunks_for(glen, NG), NG), NT, 0, ocf_cast_stream(stream)>>>(pk, B, G, glen, stats + 6 * (size_t)NG, vec);
+  return ocf_launch_status();
+}
+
+// apply pass alone, with previously computed statistics; ys[t] may live inside a wider buffer (batch stride in elements, 0 = dense)
+extern "C" int ocf_normalize_apply(const float* const* xs, float* const* ys, const long long* y_bstrides, int T, int B, int C, int H, int W,
+                                   int flags, const float* stats, ocf_stream_t stream) {
+  OCF_REQUIRE_PTR(xs); OCF_REQUIRE_PTR(ys); OCF_REQUIRE_PTR(stats);
+  OCF_REQUIRE(T > 0 && T <= MAX_T, OCF_EUNSUPPORTED);
+  OCF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, OCF_ESHAPE);
+  OCF_REQUIRE((flags & ~15) == 0, OCF_EUNSUPPORTED);
+  PtrPack pk;
+  bool vec = true;
+  for (int t = 0; t < T; ++t) {
+    OCF_REQUIRE_PTR(xs[t]); OCF_REQUIRE_PTR(ys[t]);
+    const long long bs = y_bstrides != nullptr ? y_bstrides[t] : 0;
+    OCF_REQUIRE(bs == 0 || bs >= (long long)C * H * W, OCF_ESHAPE);
+    pk.in[t] = xs[t]; pk.in2[t] = nullptr; pk.out[t] = ys[t]; pk.out_bstride[t] = bs;
+    vec = vec && ocf_aligned16(xs[t]) && ocf_aligned16(ys[t]) && (bs % 4 == 0);
+  }
+  const int G = (flags & OCF_NORM_ACROSS_CHANNELS) ? 1 : C;
+  const size_t glen = (size_t)(G == 1 ? C : 1) * H * W;
+  const long long NGll = (long long)T * B * G;
+  OCF_REQUIRE(NGll <= 65535, OCF_EUNSUPPORTED);
+  const int NG = (int)NGll;
   vec = vec && (glen % 4 == 0);
   norm_apply_kernel<<<dim3(chunks_for(glen, NG), NG), NT, 0, ocf_cast_stream(stream)>>>(pk, B, G, glen, stats + 6 * (size_t)NG, vec);
   return ocf_launch_status();
@@ -279,7 +310,7 @@ extern "C" int ocf_normalize_bwd(const float* const* grad_ys, const float* const
   bool vec = true;
   for (int t = 0; t < T; ++t) {
     OCF_REQUIRE_PTR(grad_ys[t]); OCF_REQUIRE_PTR(xs[t]); OCF_REQUIRE_PTR(grad_xs[t]);
-    pk.in[t] = grad_ys[t]; pk.in2[t] = xs[t]; pk.out[t] = grad_xs[t];
+    pk.in[t] = grad_ys[t]; pk.in2[t] = xs[t]; pk.out[t] = grad_xs[t]; pk.out_bstride[t] = 0;
     vec = vec && ocf_aligned16(grad_ys[t]) && ocf_aligned16(xs[t]) && ocf_aligned16(grad_xs[t]);
   }
   const int G = (flags & OCF_NORM_ACROSS_CHANNELS) ? 1 : C;

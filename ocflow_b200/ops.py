@@ -5,6 +5,7 @@ forward and backward below is one call into libocflow_b200.so on torch's current
 There is no CPU path: a non-CUDA or non-fp32 tensor raises TypeError.
 """
 import ctypes
+import os
 
 import torch
 
@@ -161,14 +162,19 @@ def normalize_features(feature_list, normalize=True, center=True, moments_across
 # (cost_volume_flow_net.py:171-173 and 186-190 / 201-205 / 216-220 / 231-235)
 # -------------------------------------------------------------------------------------------------
 _NORM_DEFAULT = NORM_NORMALIZE | NORM_CENTER | NORM_ACROSS_CHANNELS | NORM_ACROSS_IMAGES
+# Which correlation the fused level runs.  False (default): statistics -> apply (c1n straight into the concat buffer) -> fp32 FMA
+# correlation (TMA-fed, reads c1n in place): 4 launches, the fastest form at every FlowNetCV level on B200.  True: statistics ->
+# tcgen05 3xTF32 correlation normalising on load: 3 launches, 1e-6 instead of 1e-7 relative error, and faster only for ragged
+# row lengths (W % 4 != 0, where TMA cannot describe the rows) -- those always take it.
+LEVEL_TENSOR_CORES = os.environ.get("OCF_LEVEL_TC", "0") == "1"
 
 
 class _LevelFused(torch.autograd.Function):
     """x = cat(LeakyReLU(corr(c1n, c2n)), c1n[, up_flow, up_feat]) with [c1n, c2n] = normalize_features([c1, warp(c2, up_flow*scale)]).
 
-    3 launches forward (warp, statistics, tensor-core correlation normalising on load and writing corr + c1n straight into
-    the concat buffer) instead of 5 + torch.cat; the normalised tensors are never re-read and the two widest pieces of the
-    concat are never copied.  Backward: correlation backward (c1n read in place from the buffer), the normalisation
+    Forward: warp, statistics, apply (c1n written straight into the concat buffer), correlation reading c1n in place and writing
+    the cost volume into the same buffer -- or, with LEVEL_TENSOR_CORES / ragged rows, statistics + one tensor-core correlation
+    that normalises on load; either way no torch.cat copy of the 81 + C widest channels.  Backward: correlation backward (c1n read in place from the buffer), the normalisation
     backward through the statistics, the warp backward."""
 
     @staticmethod
@@ -190,9 +196,16 @@ class _LevelFused(torch.autograd.Function):
             f2n = torch.empty_like(c2)
             mask = torch.empty((B, 81, H, (W + 7) // 8), device=c1.device, dtype=torch.uint8)
             f1n = X[:, 81:81 + C] if has_flow else torch.empty_like(c1)
-            norm = stats[6 * NG:6 * NG + 2]      # {mean, inv_std}: one scalar pair for all groups (moments_across_images)
-            _lib.call("ocf_level_corr_fwd", _p(c1), _p(w2), _p(norm), _p(X), X.stride(0), _p(f1n), f1n.stride(0), _p(f2n), _p(mask),
-                      B, C, H, W, float(slope), _stream())
+            if LEVEL_TENSOR_CORES or W % 4 != 0:
+                norm = stats[6 * NG:6 * NG + 2]      # {mean, inv_std}: one scalar pair for all groups (moments_across_images)
+                _lib.call("ocf_level_corr_fwd", _p(c1), _p(w2), _p(norm), _p(X), X.stride(0), _p(f1n), f1n.stride(0), _p(f2n), _p(mask),
+                          B, C, H, W, float(slope), _stream())
+            else:
+                # fp32 FMA form: the apply pass leaves c1n where the concat wants it, the TMA-fed correlation reads it in place
+                bstr = (ctypes.c_longlong * 2)(f1n.stride(0), 0)
+                _lib.call("ocf_normalize_apply", ctypes.cast(_ptr_array([c1, w2]), ctypes.c_void_p), ctypes.cast(_ptr_array([f1n, f2n]), ctypes.c_void_p),
+                          ctypes.cast(bstr, ctypes.c_void_p), 2, B, C, H, W, _NORM_DEFAULT, _p(stats), _stream())
+                _lib.call("ocf_corr_fwd_strided", _p(f1n), f1n.stride(0), _p(f2n), _p(X), X.stride(0), _p(mask), B, C, H, W, float(slope), _stream())
             if has_flow:
                 X[:, 81 + C:81 + C + up_flow.shape[1]].copy_(up_flow)
                 X[:, 81 + C + up_flow.shape[1]:].copy_(up_feat)

@@ -79,7 +79,23 @@ def recording():
         calls.append(("range_map", [flow.detach()], [out[0] if with_occlusion else out], lambda f: [O.range_map(f)]))
         return out
 
+    def lf(c1, c2, up_flow=None, up_feat=None, flow_scale=1.0, leaky_slope=0.1):
+        ins = [_iso(c1), _iso(c2)] + ([_iso(up_flow), _iso(up_feat)] if up_flow is not None else [])
+        out = orig["level_fused"](*ins, flow_scale=flow_scale, leaky_slope=leaky_slope) if up_flow is not None else \
+            orig["level_fused"](ins[0], ins[1], None, None, flow_scale, leaky_slope)
+
+        def orc(a, b, fl=None, ft=None):   # cost_volume_flow_net.py:186-190 as the reference composes it
+            if fl is not None:
+                b = O.warp(b, fl * flow_scale, False)
+            an, bn = O.normalize_features([a, b])
+            corr = F.leaky_relu(O.cost_volume(an, bn, 4), leaky_slope)
+            return [corr if fl is None else torch.cat((corr, an, fl, ft), 1)]
+        calls.append(("level_fused", ins, [out], orc))
+        return out
+
+    orig["level_fused"] = ops.level_fused
     ops.cost_volume, ops.normalize_features, ops.warp, ops.occ_photo_fused, ops.smoothness_loss, ops.range_map = cv, nf, wp, opf, sm, rm
+    ops.level_fused = lf
     try:
         yield calls
     finally:

@@ -1,5 +1,5 @@
-"""GPU: the fused FlowNetCV level op (ops.level_fused: warp -> statistics -> tensor-core correlation normalising on load,
-writing into the concat buffer) against the fp64 oracle chain of cost_volume_flow_net.py:186-190, outputs and gradients,
+"""GPU: the fused FlowNetCV level op (ops.level_fused: warp -> statistics -> [apply -> fp32 FMA correlation | tensor-core
+correlation normalising on load], writing into the concat buffer) against the fp64 oracle chain of cost_volume_flow_net.py:186-190, outputs and gradients,
 at pyramid-level shapes (regular and ragged), with and without the warp (coarsest level)."""
 import pytest
 import torch
@@ -18,10 +18,15 @@ def _chain(c1, c2, up_flow, up_feat, scale):
     return corr if up_flow is None else torch.cat((corr, c1n, up_flow, up_feat), 1)
 
 
+@pytest.mark.parametrize("tensor_cores", [False, True])
 @pytest.mark.parametrize("B,C,H,W,with_flow", [(2, 32, 24, 32, True), (1, 196, 6, 8, False), (2, 16, 47, 39, True), (3, 128, 12, 16, True),
                                                (2, 64, 48, 64, True), (1, 96, 9, 311, True), (2, 8, 16, 8, False)])
-def test_level_fused_matches_oracle_chain(B, C, H, W, with_flow):
+def test_level_fused_matches_oracle_chain(B, C, H, W, with_flow, tensor_cores, monkeypatch):
     from ocflow_b200 import ops
+
+    # both forms of the level: statistics -> apply -> fp32 FMA correlation (default) and statistics -> tcgen05 correlation that
+    # normalises on load (ragged rows always take the latter)
+    monkeypatch.setattr(ops, "LEVEL_TENSOR_CORES", tensor_cores)
 
     g = torch.Generator().manual_seed(B * 7919 + C * 31 + H * 7 + W)
     c1 = torch.randn(B, C, H, W, generator=g) * 1.7 + 0.8       # un-normalised features: mean and std away from (0, 1)
