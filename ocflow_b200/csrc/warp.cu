@@ -112,7 +112,7 @@ warp_fwd_kernel(const float* __restrict__ img, const float* __restrict__ flow, c
     // serialises the load latencies -- seen in the SASS of an earlier version): the tail is a predicated store
 #pragma unroll
     for (int j = 0; j < CB; ++j) {
-      float r = 0.f;   // tap order of ATen's grid_sampler: nw, ne, sw, se
+      float r = 0.f;   // ATen's tap order: nw, ne, sw, se
       r = fmaf(vnw ? a[j][0] : 0.f, wnw, r);
       r = fmaf(vne ? a[j][1] : 0.f, wne, r);
       r = fmaf(vsw ? a[j][2] : 0.f, wsw, r);
