@@ -579,7 +579,7 @@ def main():
     torch.backends.cudnn.allow_tf32 = bool(args.tf32)
     torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
     B, H, W = args.batch, args.height, args.width
-    model = build_model(seed=0)
+    model = build_model({"conv_math": "tf32" if args.tf32 else "fp32"}, seed=0)
     if args.channels_last:
         model = model.to(memory_format=torch.channels_last)
     step = TrainStep(model, use_graph=bool(args.graph))
@@ -658,9 +658,10 @@ def main():
     dte = float(dte)
 
     def finish():
-        # Every rank leaves together and WITHOUT tearing the NCCL communicator down: the step's CUDA graph holds the
-        # captured all-reduce, and destroy_process_group() under that graph does not return (observed on B200 x2).
-        # Ranks > 0 wait (file flag, no collective) until rank 0 has printed its line, then all exit hard with status 0.
+        # Clean shutdown: rank 0 prints first (ranks > 0 wait on a file flag, no collective), then every rank drops the step's
+        # CUDA graph -- it holds the captured NCCL all-reduce, and destroy_process_group() under a live graph does not return
+        # (observed on B200 x2) -- synchronises and destroys the process group.  A watchdog thread turns a teardown that still
+        # hangs into a hard exit with status 0, so the driver never waits on it.
         sys.stdout.flush()
         sys.stderr.flush()
         if world > 1:
@@ -671,8 +672,18 @@ def main():
                 t_end = time.time() + 600
                 while not os.path.exists(flag) and time.time() < t_end:
                     time.sleep(0.05)
-            torch.cuda.synchronize()
-            os._exit(0)
+            import threading
+
+            def _hard_exit():
+                sys.stderr.write("bench.py rank %d: NCCL teardown did not return within 30 s, exiting hard\n" % rank)
+                sys.stderr.flush()
+                os._exit(0)
+            dog = threading.Timer(30.0, _hard_exit)
+            dog.daemon = True
+            dog.start()
+            step.close()
+            dist.destroy_process_group()
+            dog.cancel()
 
     if rank != 0:
         finish()
@@ -731,12 +742,12 @@ def main():
     # precision cost of the policy is visible next to its speed.
     if world == 1 and not args.skip_alt and not args.tf32:
         with torch.no_grad():
-            ref_model = build_model(seed=0)
+            ref_model = build_model({"conv_math": "fp32"}, seed=0)
             l32 = float(ref_model.training_step(batch, 0))
-            torch.backends.cudnn.allow_tf32 = True
+            ref_model = build_model({"conv_math": "tf32"}, seed=0)
             ltf = float(ref_model.training_step(batch, 0))
         del ref_model
-        alt_step = TrainStep(build_model(seed=0), use_graph=bool(args.graph))
+        alt_step = TrainStep(build_model({"conv_math": "tf32"}, seed=0), use_graph=bool(args.graph))
         for _ in range(3):
             alt_step.step(batch)
         torch.cuda.synchronize()
@@ -747,9 +758,8 @@ def main():
         a1.record()
         torch.cuda.synchronize()
         adt = a0.elapsed_time(a1) * 1e-3
-        torch.backends.cudnn.allow_tf32 = False
         line["alt_tf32_convs"] = {"value": B * args.steps / adt, "unit": UNIT, "ms_per_step": 1e3 * adt / args.steps,
-                                  "conv_math": "tf32 (torch's default cudnn.allow_tf32=True); hot-path kernels unchanged (fp32)",
+                                  "conv_math": "hparams['conv_math'] = 'tf32' (torch's default cudnn.allow_tf32=True); hot-path kernels unchanged (fp32)",
                                   "step0_loss_fp32": l32, "step0_loss_tf32": ltf, "step0_loss_rel_diff": abs(ltf - l32) / abs(l32)}
         del alt_step
 

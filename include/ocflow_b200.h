@@ -127,6 +127,18 @@ int ocf_normalize_bwd(const float* const* grad_ys, const float* const* xs, float
                       ocf_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Bilinear resampling, align_corners=True.  Replaces the two F.interpolate calls either side of the hot path:
+ *   F.interpolate(flow2, scale_factor=4, mode='bilinear', align_corners=True) * 20   (cost_volume_flow_net.py:245; mul = 20)
+ *   F.interpolate(img1, scale_factor=0.25, mode='bilinear', align_corners=True)      (models/model.py:396)
+ * in [planes, Hi, Wi] -> out [planes, Ho, Wo] (planes = B*C), out = mul * bilinear(in); ATen's upsample_bilinear2d
+ * arithmetic.  The backward is a gather (no atomics): grad_in [planes, Hi, Wi] is fully written.
+ * ------------------------------------------------------------------------------------------- */
+int ocf_resize_bilinear_fwd(const float* in, float* out, int planes, int Hi, int Wi, int Ho, int Wo, float mul,
+                            ocf_stream_t stream);
+int ocf_resize_bilinear_bwd(const float* grad_out, float* grad_in, int planes, int Hi, int Wi, int Ho, int Wo, float mul,
+                            ocf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Bilinear backward warp.  Replaces the 11 `warp`/`backwarp` bodies:
  *   align_corners=1: utils.py:20-58 (is_mask), models/model.py:191-221, 962-992, 1159-1189,
  *                    models/flow_model.py:49-79, models/networks/pwc_net.py:6-29

@@ -962,11 +962,17 @@ using Tile4P = CorrTile<4, 8, 4, 8, 8, OCF_FWD_STAGES>;  // persistent forward: 
 constexpr int BWD_CR = 4;
 constexpr int FWD_UNROLL = OCF_FWD_UNROLL;
 
+// opt-in to > 48 KB of dynamic shared memory, once per kernel instantiation and size (the attribute is sticky; eager callers --
+// the patched reference runs without a CUDA graph -- used to pay the driver call on every launch)
 template <class K>
 int set_smem(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024) {
+  static size_t done_for = 0;   // one instance per K (function-pointer type is not unique per kernel, hence the pointer check)
+  static K done_kernel = nullptr;
+  if (bytes > 48 * 1024 && !(done_kernel == kernel && done_for == bytes)) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
+    done_kernel = kernel;
+    done_for = bytes;
   }
   return 0;
 }
@@ -1037,7 +1043,40 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 // NCHW fp32 tensor [B, C, H, W] -> 4-D tensor map with a {bw, bh, cc, 1} box; out-of-bounds elements read as zero
+// Descriptors are pure functions of (pointer, shape, box, stride): the last few are kept per host thread, so a training loop
+// that re-presents the same activations (torch's caching allocator hands back the same blocks every step) encodes each map once.
+struct MapKey {
+  const float* base;
+  int B, C, H, W, bw, bh, cc;
+  long long bstride;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && B == o.B && C == o.C && H == o.H && W == o.W && bw == o.bw && bh == o.bh && cc == o.cc && bstride == o.bstride;
+  }
+};
+constexpr int MAP_CACHE = 64;
+struct MapCache {
+  MapKey key[MAP_CACHE];
+  CUtensorMap map[MAP_CACHE];
+  int used = 0, next = 0;
+};
+
+bool make_map_uncached(CUtensorMap* map, const float* base, int B, int C, int H, int W, int bw, int bh, int cc, long long bstride);
+
 bool make_map(CUtensorMap* map, const float* base, int B, int C, int H, int W, int bw, int bh, int cc, long long bstride = 0) {
+  static thread_local MapCache cache;
+  const MapKey k{base, B, C, H, W, bw, bh, cc, bstride};
+  for (int i = 0; i < cache.used; ++i)
+    if (cache.key[i] == k) { *map = cache.map[i]; return true; }
+  if (!make_map_uncached(map, base, B, C, H, W, bw, bh, cc, bstride)) return false;
+  const int slot = cache.next;
+  cache.key[slot] = k;
+  cache.map[slot] = *map;
+  cache.next = (slot + 1) % MAP_CACHE;
+  if (cache.used < MAP_CACHE) ++cache.used;
+  return true;
+}
+
+bool make_map_uncached(CUtensorMap* map, const float* base, int B, int C, int H, int W, int bw, int bh, int cc, long long bstride) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (fn == nullptr) return false;
   const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};

@@ -5,14 +5,13 @@ checkpoint loads unchanged and `torch.manual_seed(s)` yields the reference's ini
 `forward(x[B,6,H,W]) -> (flow1 [B,2,H,W] pixels, flow_l2 [B,2,H/4,W/4] quarter-res pixels)`.
 
 Per pyramid level the reference runs warp -> normalize_features -> compute_cost_volume -> LeakyReLU -> cat as ~1000 ATen
-launches; here it is ONE fused op of 3 launches (`ops.level_fused`: warp with the `up_flow*scale` folded in, one
-statistics pass, and a tensor-core correlation that normalises its operands on load and writes the cost volume and the
-normalised c1 straight into the decoder's concat buffer).  The convolution stacks stay on cuDNN (out of scope, SURVEY.md
-section 2).
+launches; here it is ONE fused op of 4 launches (`ops.level_fused`: warp with the `up_flow*scale` folded in, one
+statistics pass, an apply pass that leaves the normalised c1 where the decoder's concat wants it, and the correlation,
+which reads it in place and writes the cost volume into the same buffer).  The convolution stacks stay on cuDNN (out of
+scope); the x4 flow up-sampling at the end (:245) is `ops.resize_bilinear`.
 """
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import ops
 
@@ -117,7 +116,7 @@ class FlowNetCV(nn.Module):
         for i in range(1, 7):
             t = getattr(self, "dc_conv%d" % i)(t)
         flow2 = flow + self.dc_conv7(t)
-        flow1 = F.interpolate(flow2, scale_factor=4, mode="bilinear", align_corners=True) * 20
+        flow1 = ops.resize_bilinear(flow2, scale_factor=4, mul=20.0)      # F.interpolate(..., align_corners=True) * 20, :245
         return flow1, flow2 * 5.0
 
     def forward(self, x):

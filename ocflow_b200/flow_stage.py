@@ -10,11 +10,23 @@ photometric(1-occ) -> mse -> bce (≈120 ATen launches and 4 host syncs in the r
 """
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 from torch.optim import Adam
 
 from . import ops
 from .flow_net_cv import FlowNetCV
+
+
+class _ConvMath:
+    def __init__(self, allow_tf32):
+        self.allow = bool(allow_tf32)
+
+    def __enter__(self):
+        self.old = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = self.allow
+
+    def __exit__(self, *exc):
+        torch.backends.cudnn.allow_tf32 = self.old
+        return False
 
 
 class FlowStageModel(nn.Module):
@@ -31,6 +43,12 @@ class FlowStageModel(nn.Module):
         self.displacement = hparams.get("displacement", 4)
         # not a reference hyper-parameter: False evaluates the network twice exactly as models/model.py:380-386 is written
         self.share_encoder = hparams.get("share_encoder", True)
+        # not a reference hyper-parameter: math of the cuDNN convolution stacks (the hot-path kernels are fp32 either way).
+        # 'fp32' = strict IEEE fp32 convolutions, the parity mode (matches the reference's CPU results to the tolerances of
+        # tests/); 'tf32' = torch's own default on Ampere+ (cudnn.allow_tf32), i.e. what the unmodified reference gets on a GPU
+        self.conv_math = hparams.get("conv_math", "fp32")
+        if self.conv_math not in ("fp32", "tf32"):
+            raise ValueError("conv_math must be 'fp32' or 'tf32' (got %r)" % (self.conv_math,))
         model = hparams.get("model", "simple")
         self.model = model
         if model != "pwc":
@@ -70,7 +88,7 @@ class FlowStageModel(nn.Module):
         raise ValueError("Not supported dataset")
 
     def _smoothness(self, img1, flow_l2):
-        img1_l2 = F.interpolate(img1, scale_factor=0.25, mode="bilinear", align_corners=True)
+        img1_l2 = ops.resize_bilinear(img1, scale_factor=0.25)            # F.interpolate(..., align_corners=True), :396
         smooth1 = ops.smoothness_loss(img1_l2, flow_l2, 1)
         smooth2 = ops.smoothness_loss(img1_l2, flow_l2, 2)
         return smooth1, smooth2
@@ -112,7 +130,16 @@ class FlowStageModel(nn.Module):
             return photo, smooth1, smooth2, flow_error, photo_occ, occ_error
         return photo, smooth1, smooth2, flow_error, photo_occ
 
+    def conv_math_scope(self):
+        """Context manager applying hparams['conv_math'] to the cuDNN convolutions run inside it.  The flag is read when a
+        convolution is DISPATCHED, so a backward pass must run inside the scope as well (train.TrainStep does)."""
+        return _ConvMath(self.conv_math == "tf32")
+
     def _losses(self, batch, batch_idx, mode):
+        with self.conv_math_scope():
+            return self._losses_impl(batch, batch_idx, mode)
+
+    def _losses_impl(self, batch, batch_idx, mode):
         if not self.occ_aware:
             if not self.with_occ:
                 return self.general_step(batch, batch_idx, mode)

@@ -314,6 +314,43 @@ def warp(img, flow, align_corners=True, is_mask=False, occ=None, flow_scale=1.0)
 
 
 # -------------------------------------------------------------------------------------------------
+# bilinear resize, align_corners=True (the F.interpolate glue of cost_volume_flow_net.py:245 and models/model.py:396)
+# -------------------------------------------------------------------------------------------------
+class _Resize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, Ho, Wo, mul):
+        B, C, Hi, Wi = x.shape
+        out = torch.empty((B, C, Ho, Wo), device=x.device, dtype=torch.float32)
+        with torch.cuda.device_of(x):
+            _lib.call("ocf_resize_bilinear_fwd", _p(x), _p(out), B * C, Hi, Wi, Ho, Wo, float(mul), _stream())
+        ctx.cfg = (B, C, Hi, Wi, Ho, Wo, float(mul))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, C, Hi, Wi, Ho, Wo, mul = ctx.cfg
+        g = g.contiguous()
+        gin = torch.empty((B, C, Hi, Wi), device=g.device, dtype=torch.float32)
+        with torch.cuda.device_of(g):
+            _lib.call("ocf_resize_bilinear_bwd", _p(g), _p(gin), B * C, Hi, Wi, Ho, Wo, mul, _stream())
+        return gin, None, None, None
+
+
+def resize_bilinear(x, size=None, scale_factor=None, mul=1.0):
+    """mul * F.interpolate(x, size / scale_factor, mode='bilinear', align_corners=True) in one launch (gather backward)."""
+    x = _req(x, "x", 4)
+    if (size is None) == (scale_factor is None):
+        raise ValueError("exactly one of size and scale_factor must be given")
+    if size is None:
+        Ho, Wo = int(x.shape[2] * scale_factor), int(x.shape[3] * scale_factor)   # floor, as F.interpolate
+    else:
+        Ho, Wo = (int(size), int(size)) if isinstance(size, int) else (int(size[0]), int(size[1]))
+    if Ho < 1 or Wo < 1:
+        raise ValueError("output size must be positive (got %dx%d)" % (Ho, Wo))
+    return _Resize.apply(x, Ho, Wo, float(mul))
+
+
+# -------------------------------------------------------------------------------------------------
 # range map / occlusion  (forward only: the reference calls it under no_grad, models/model.py:381-391)
 # -------------------------------------------------------------------------------------------------
 def range_map(flow, with_occlusion=False):

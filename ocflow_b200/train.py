@@ -10,6 +10,8 @@ kernel directly, so there is nothing to fuse a collective into.)
 The whole step (2 network forwards, loss kernels, backward, all-reduce, Adam) can be captured in one CUDA graph
 (`use_graph=True`): shapes are static, every C-ABI call enqueues on torch's current stream and never synchronises.
 """
+import contextlib
+
 import torch
 import torch.distributed as dist
 
@@ -66,11 +68,23 @@ class TrainStep:
 
     def _eager(self, batch):
         self.grads.zero_()
-        loss = self.model.training_step(batch, 0)
-        loss.backward()
+        scope = self.model.conv_math_scope() if hasattr(self.model, "conv_math_scope") else contextlib.nullcontext()
+        with scope:   # forward AND backward convolutions under hparams['conv_math']
+            loss = self.model.training_step(batch, 0)
+            loss.backward()
         self.grads.all_reduce_mean(self.group)
         self.opt.step()
         return loss.detach()
+
+    def close(self):
+        """Release the captured graph (it holds the NCCL all-reduce of the step: the process group cannot be destroyed while
+        a graph that references its communicator is alive) and wait for the device.  After this,
+        torch.distributed.destroy_process_group() returns normally."""
+        self.graph = None
+        self.static_loss = None
+        self.static_batch = None
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
 
     def _capture(self, batch):
         self.static_batch = tuple(t.clone() for t in batch)

@@ -147,6 +147,31 @@ def warp(img, flow, align_corners=True, is_mask=False):
 # --------------------------------------------------------------------------------------------
 
 
+def resize_bilinear(x, size=None, scale_factor=None):
+    """F.interpolate(x, size / scale_factor, mode='bilinear', align_corners=True) restated from ATen's upsample_bilinear2d
+    (aten/src/ATen/native/UpSample.h: area_pixel_compute_scale, compute_source_index_and_lambda): the glue calls of
+    models/networks/cost_volume_flow_net.py:245 and models/model.py:396.  Pinned against F.interpolate itself in
+    tests/test_oracle_golden.py."""
+    B, C, Hi, Wi = x.shape
+    if size is None:
+        Ho, Wo = int(Hi * scale_factor), int(Wi * scale_factor)
+    else:
+        Ho, Wo = (size, size) if isinstance(size, int) else size
+
+    def axis(n_in, n_out):
+        r = (n_in - 1) / (n_out - 1) if n_out > 1 else 0.0
+        src = torch.arange(n_out, dtype=x.dtype) * torch.tensor(r, dtype=x.dtype)
+        i0 = src.floor().long().clamp(max=n_in - 1)
+        i1 = i0 + (i0 < n_in - 1).long()
+        l1 = src - i0.to(x.dtype)
+        return i0, i1, 1.0 - l1, l1
+    y0, y1, ly0, ly1 = axis(Hi, Ho)
+    x0, x1, lx0, lx1 = axis(Wi, Wo)
+    top = x[:, :, y0][:, :, :, x0] * lx0 + x[:, :, y0][:, :, :, x1] * lx1
+    bot = x[:, :, y1][:, :, :, x0] * lx0 + x[:, :, y1][:, :, :, x1] * lx1
+    return top * ly0[:, None] + bot * ly1[:, None]
+
+
 def flow_to_warp(flow_bhw2):
     """Endpoints (x+u, y+v) of a [B,H,W,2] flow (models/model.py:223-241)."""
     B, H, W, _ = flow_bhw2.shape
@@ -426,7 +451,7 @@ def flownetcv_forward(sd, x, displacement=4):
     for name, dil in (("dc_conv1", 1), ("dc_conv2", 2), ("dc_conv3", 4), ("dc_conv4", 8), ("dc_conv5", 16), ("dc_conv6", 1)):
         t = _conv_lrelu(sd, name, t, padding=dil, dilation=dil)
     flow2 = flow + F.conv2d(t, sd["dc_conv7.weight"], sd["dc_conv7.bias"], padding=1)
-    flow1 = F.interpolate(flow2, scale_factor=4, mode="bilinear", align_corners=True) * 20
+    flow1 = resize_bilinear(flow2, scale_factor=4) * 20
     return flow1, flow2 * 5.0
 
 
@@ -445,7 +470,7 @@ def occ_aware_step(sd, batch, displacement=4):
         back_flow, _ = flownetcv_forward(sd, torch.cat((img2, img1), 1), displacement)
         occ_pred = occlusion_from_range_map(range_map(back_flow))
     photo = photometric_error(img_warped, img1, occ_pred)
-    img1_l2 = F.interpolate(img1, scale_factor=0.25, mode="bilinear", align_corners=True)
+    img1_l2 = resize_bilinear(img1, scale_factor=0.25)
     smooth1 = first_order_smoothness_loss(img1_l2, flow_l2)
     smooth2 = second_order_smoothness_loss(img1_l2, flow_l2)
     flow_error = ((flow_pred - flow_gt) ** 2).mean()

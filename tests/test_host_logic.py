@@ -118,3 +118,25 @@ def test_product_never_imports_oracle_or_falls_back():
                 code = "\n".join(l for l in src.splitlines() if not l.strip().startswith(("#", "//", '"""')))
                 m = bad.search(re.sub(r'""".*?"""', "", code, flags=re.S))
                 assert m is None, "%s: %r" % (fn, m.group(0))
+
+
+def test_conv_math_hparam_is_validated_and_scoped():
+    """hparams['conv_math'] (not a reference hyper-parameter): 'fp32' is the parity mode, 'tf32' torch's default conv math;
+    the scope sets cudnn.allow_tf32 for the convolutions dispatched inside it and restores the previous value."""
+    import torch
+
+    from ocflow_b200.flow_stage import FlowStageModel
+
+    with pytest.raises(ValueError):
+        FlowStageModel({"model": "pwc", "learning_rate": 1e-3, "conv_math": "bf16"})
+    old = torch.backends.cudnn.allow_tf32
+    try:
+        for mode, want in (("fp32", False), ("tf32", True)):
+            m = FlowStageModel({"model": "pwc", "learning_rate": 1e-3, "conv_math": mode})
+            torch.backends.cudnn.allow_tf32 = not want
+            with m.conv_math_scope():
+                assert torch.backends.cudnn.allow_tf32 is want
+            assert torch.backends.cudnn.allow_tf32 is (not want)
+        assert FlowStageModel({"model": "pwc", "learning_rate": 1e-3}).conv_math == "fp32"
+    finally:
+        torch.backends.cudnn.allow_tf32 = old

@@ -56,6 +56,7 @@ def _oracle_ops():
         return corr if up_flow is None else torch.cat((corr, c1n, up_flow, up_feat), 1)
 
     ns.level_fused = level_fused
+    ns.resize_bilinear = lambda x, size=None, scale_factor=None, mul=1.0: O.resize_bilinear(x, size, scale_factor) * mul
     ns.warp, ns.cost_volume, ns.range_map, ns.occ_photo_fused = warp, cost_volume, range_map, occ_photo_fused
     ns.smoothness_loss, ns.pair_loss = smoothness_loss, pair_loss
     ns.normalize_features = lambda fl, **kw: O.normalize_features(fl, **kw)
