@@ -1089,6 +1089,10 @@ bool make_map_uncached(CUtensorMap* map, const float* base, int B, int C, int H,
 
 }  // namespace
 
+bool ocf_make_tensor_map(CUtensorMap* map, const float* base, int B, int C, int H, int W, int bw, int bh, int cc, long long bstride) {
+  return make_map(map, base, B, C, H, W, bw, bh, cc, bstride);
+}
+
 // f1_bstride: batch stride of f1 in elements (0 = dense) -- the fused level op keeps the normalised first feature map inside
 // the decoder's concat buffer (ops.level_fused); only the TMA path (d = 4, 16-byte aligned rows) reads it in place
 static int corr_fwd_impl(const float* f1, long long f1_bstride, const float* f2, float* out, int B, int C, int H, int W, int d,

@@ -22,17 +22,17 @@ def run(f1, f2, slope=0.1, norm=None, want_mask=True):
     out = torch.full((B, 81, H, W), float("nan"), device="cuda")
     mask = torch.zeros(B, 81, H, (W + 7) // 8, device="cuda", dtype=torch.uint8) if want_mask else None
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    _lib.call("ocf_corr_fwd", P(f1), P(f2), P(out), B, C, H, W, 4, 0, slope, P(norm), P(mask), st)
+    _lib.call("ocf_level_corr_fwd", P(f1), P(f2), P(norm), P(out), 0, None, 0, None, P(mask), B, C, H, W, slope, st)
     torch.cuda.synchronize()
     return out, mask
 
 
 def main():
     torch.manual_seed(0)
-    print("OCF_CORR_TC =", os.environ.get("OCF_CORR_TC", "(default 1)"))
+    print("tensor-core correlation forward (ocf_level_corr_fwd); OCF_TC_NO_TMA =", os.environ.get("OCF_TC_NO_TMA", "0"))
     worst = 0.0
     for (B, C, H, W) in [(1, 8, 16, 8), (2, 32, 24, 32), (1, 196, 6, 8), (2, 16, 47, 39), (1, 3, 33, 65), (2, 64, 12, 20), (1, 1, 1, 1),
-                         (1, 5, 2, 3), (1, 96, 9, 311), (3, 128, 12, 16), (8, 32, 96, 128), (2, 16, 188, 621)]:
+                         (1, 5, 2, 3), (1, 96, 9, 311), (3, 128, 12, 16), (8, 32, 96, 128), (2, 16, 188, 621), (2, 13, 40, 52), (1, 70, 20, 12)]:
         f1 = torch.randn(B, C, H, W)
         f2 = torch.randn(B, C, H, W) + 0.3
         ref = torch.nn.functional.leaky_relu(O.cost_volume(f1.double(), f2.double(), 4), 0.1)
@@ -72,7 +72,7 @@ def main():
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            _lib.call("ocf_corr_fwd", P(f1), P(f2), P(out), B, C, H, W, 4, 0, 0.1, None, P(mask), st)
+            _lib.call("ocf_level_corr_fwd", P(f1), P(f2), None, P(out), 0, None, 0, None, P(mask), B, C, H, W, 0.1, st)
             e1.record()
             torch.cuda.synchronize()
             if i >= 3:
