@@ -717,7 +717,11 @@ def main():
         us = live[dom][0]
         gbs = kt[dom]["bytes"] / (us * 1e-6) / 1e9
         line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                            "traffic": ncu_traffic(dom), "peak_source": peak_src, "launch_us": us,
+                            "traffic": ncu_traffic(dom), "traffic_l2": ncu_traffic("lts:" + dom),
+                            "traffic_note": "traffic = dram__bytes_read + dram__bytes_write of one launch under ncu (cold caches; output "
+                                            "lines still dirty in the 126 MB L2 at kernel end are not counted as DRAM writes); traffic_l2 = "
+                                            "lts__t_sectors x 32 B (all bytes through the L2, reads + writes) of the same launch",
+                            "peak_source": peak_src, "launch_us": us,
                             "algorithmic_bytes": kt[dom]["bytes"], "launches_per_step": live[dom][1],
                             "timing": ("mean over the launches of 3 eager training steps, CUDA events around each C-ABI call on its "
                                        "launching stream (inputs as the step leaves them in L2)") if world == 1 else

@@ -649,7 +649,9 @@ corr_fwd_generic(const float* __restrict__ f1, const float* __restrict__ f2, flo
 // ---- backward -----------------------------------------------------------------------------------
 // mode 0: dout = d f1, fo = f2 ; mode 1: dout = d f2, fo = f1.
 // blockIdx.z = (b * nmodes + slot) * ksplit + channel slice.
-template <class T, int CR, int STG>
+// GDIRECT (TMA staging only, experiment): the 81 coefficient planes go global -> registers with 128-bit loads instead of through a
+// TMA-staged shared-memory copy, so that the feature ring starts filling at kernel entry.  Measured slower, see the launcher.
+template <class T, int CR, int STG, bool GDIRECT = false>
 __global__ void __launch_bounds__(Threads<T, STG>::value, 2)
 corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
                const __grid_constant__ CUtensorMap mapg, const float* __restrict__ g,
@@ -696,6 +698,7 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
     const bool has_act = oact != nullptr || mask != nullptr;
     if (dyi == ND) {
       if (lane == 0) {
+        if constexpr (!GDIRECT) {
         // coefficient boxes: mode 0 -> planes dy*ND.. at (y0, x0) ; mode 1 -> planes (2D-dy)*ND.. at (y0+dy-D, x0-D)
         constexpr unsigned GBYTES = sizeof(float) * ND * BOXG;
         mbar_expect_tx(&g_bar, GBYTES);
@@ -704,6 +707,7 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
           tma_load_4d(smem + w * BOXG, &mapg, &g_bar, mode == 0 ? x0 : x0 - D, mode == 0 ? y0 : y0 + w - D, plane0, b);
         }
         mbar_wait(&gdone_bar, 0);  // every warp has lifted its coefficients out of the staging area: feed the feature ring
+        }
         constexpr unsigned BYTES = sizeof(float) * T::F2_STAGE;
         const CUtensorMap* map = mode == 0 ? &map2 : &map1;  // the OTHER feature
         for (int i = 0; i < nchunks; ++i) {
@@ -774,6 +778,43 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
         }
       }
     }
+    if constexpr (GDIRECT) {
+      // W % 4 == 0 on this path: an aligned group of 4 columns is entirely inside or entirely outside the row
+      const float* gp = g + gb;
+      const int xs = x0 + tx * PX;
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (mode == 0) {
+        const int y = y0 + ty;
+#pragma unroll
+        for (int dx = 0; dx < ND; ++dx) {
+          const float* row = gp + ((size_t)(dyi * ND + dx) * H + min(y, H - 1)) * W;
+#pragma unroll
+          for (int q = 0; q < PX / 4; ++q) {
+            const int x = xs + 4 * q;
+            const float4 v = (y < H && x < W) ? __ldg(reinterpret_cast<const float4*>(row + x)) : z4;
+            G[dx][4 * q] = v.x; G[dx][4 * q + 1] = v.y; G[dx][4 * q + 2] = v.z; G[dx][4 * q + 3] = v.w;
+          }
+        }
+      } else {
+        const int sy = y0 + ty + dyi - D;
+        const bool yok = sy >= 0 && sy < H;
+#pragma unroll
+        for (int dx = 0; dx < ND; ++dx) {
+          const float* row = gp + ((size_t)((2 * D - dyi) * ND + (2 * D - dx)) * H + min(max(sy, 0), H - 1)) * W;
+          const int cb = xs - D + (dx & ~3);   // aligned group holding the first needed column xs + dx - D
+          float t[PX + 4];
+#pragma unroll
+          for (int q = 0; q < PX / 4 + 1; ++q) {
+            const int x = cb + 4 * q;
+            const bool need = q < PX / 4 || (dx & 3) != 0;   // the third group only when the window is not aligned
+            const float4 v = (need && yok && x >= 0 && x < W) ? __ldg(reinterpret_cast<const float4*>(row + x)) : z4;
+            t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
+          }
+#pragma unroll
+          for (int p = 0; p < PX; ++p) G[dx][p] = t[p + (dx & 3)];
+        }
+      }
+    } else {
     const float* gw = smem + dyi * BOXG + ty * GW + tx * PX;
     mbar_wait(&g_bar, 0);
     if (mode == 0) {
@@ -800,6 +841,7 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&gdone_bar);
+    }
     if (has_act) {
 #pragma unroll
       for (int dx = 0; dx < ND; ++dx)
@@ -1202,7 +1244,16 @@ int ocf_corr_bwd_impl(const float* grad_out, const float* out_act, const float* 
     tma = tma && (f1_bstride % 4 == 0) && (f2_bstride % 4 == 0);
     tma = tma && make_map(&m1, f1, B, C, H, W, T::S2, T::F2H, T::CC, f1_bstride) && make_map(&m2, f2, B, C, H, W, T::S2, T::F2H, T::CC, f2_bstride) &&
           make_map(&mg, grad_out, B, (int)(nd * nd), H, W, T::S2, T::TH, T::ND, gbs);
-    if (tma) {
+    // developer knob (A/B runs): OCF_BWD_GDIRECT=1 loads the coefficients global -> registers.  Measured: SLOWER (L2 level 70.3 vs
+    // 61.3 us, L3 43.0 vs 38.8): with 96 registers per thread only ~5 of the 18-24 128-bit loads are in flight, so the lift costs
+    // several L2 round trips instead of one TMA round trip.  The staged form stays the default.
+    static const int gdirect = []() { const char* e = getenv("OCF_BWD_GDIRECT"); return e ? atoi(e) : 0; }();
+    if (tma && gdirect) {
+      auto kernel = corr_bwd_tiled<T, BWD_CR, STG_TMA, true>;
+      if (int e = set_smem(kernel, smem)) return e;
+      if (int e = launch_kernel(kernel, grid, T::THREADS + 32, smem, s, 1, m1, m2, mg, grad_out, out_act, mask, f1, f2, df1, df2, C, H, W, g_bstride,
+                                act_bstride, inv_c, leaky_slope, nmodes, first, ks, f1_bstride, f2_bstride)) return e;
+    } else if (tma) {
       const size_t gstage = sizeof(float) * T::ND * T::ND * T::TH * T::S2;  // coefficient staging, reused by ring + red
       if (gstage > smem) smem = gstage;
       auto kernel = corr_bwd_tiled<T, BWD_CR, STG_TMA>;

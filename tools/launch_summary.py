@@ -22,7 +22,7 @@ for r in rows[h + 1:]:
     a[1] += us
     total += us
     n += 1
-mine = ("corr_", "warp_", "range_map", "occ_photo", "norm_", "group_sums", "smooth_", "photometric", "robust_l1", "pair_loss", "gradient_kernel", "flow_to_warp", "occ_from_range")
+mine = ("corr_", "warp_", "range_map", "occ_photo", "norm_", "group_sums", "smooth_", "photometric", "robust_l1", "pair_loss", "gradient_kernel", "flow_to_warp", "occ_from_range", "resize_", "pack_pairs")
 print("launches %d   total kernel time %.1f us" % (n, total))
 mt = sum(v[1] for k, v in agg.items() if k.startswith(mine))
 mc = sum(v[0] for k, v in agg.items() if k.startswith(mine))
