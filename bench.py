@@ -393,6 +393,21 @@ def extra_kernel_rows(args, torch, peak):
                 rows["kitti_188x%d_B8_C%d_%s" % (w, C, name)] = {"us": round(t * 1e6, 1), "gbs": round(nbytes / t / 1e9, 1), "frac": round(nbytes / t / 1e9 / peak, 3),
                                                                "tflops": round(flops / t / 1e12, 2) if flops else None}
             del f1, f2, out, gout, msk, d1, d2, wout, dfl, cases
+    # max_displacement = 10 (441 planes): the FlowNetC-family correlation (conv3 features: 256 channels at 1/8 resolution)
+    for C, hh, ww in ((256, 48, 64),):
+        n = B * hh * ww
+        f1 = torch.randn(B, C, hh, ww, device="cuda", generator=g)
+        f2 = torch.randn(B, C, hh, ww, device="cuda", generator=g)
+        out = torch.empty(B, 441, hh, ww, device="cuda")
+        gout = torch.randn(B, 441, hh, ww, device="cuda", generator=g)
+        d1, d2 = torch.empty_like(f1), torch.empty_like(f2)
+        t = timed(lambda: _lib.call("ocf_corr_fwd", P(f1), P(f2), P(out), B, C, hh, ww, 10, 0, 0.1, None, None, st))
+        rows["corr_d10_fwd_%dx%d_B8_C%d" % (hh, ww, C)] = {"us": round(t * 1e6, 1), "frac": round(4 * n * (2 * C + 441) / t / 1e9 / peak, 3),
+                                                          "tflops": round(2 * 441 * C * n / t / 1e12, 2)}
+        t = timed(lambda: _lib.call("ocf_corr_bwd", P(gout), P(out), P(f1), P(f2), P(d1), P(d2), B, C, hh, ww, 10, 0, 0, 0.1, None, st), reps=3)
+        rows["corr_d10_bwd_%dx%d_B8_C%d" % (hh, ww, C)] = {"us": round(t * 1e6, 1), "frac": round(4 * n * (2 * 441 + 4 * C) / t / 1e9 / peak, 3),
+                                                                  "tflops": round(4 * 441 * C * n / t / 1e12, 2)}
+        del f1, f2, out, gout, d1, d2
     # tensor-core (tcgen05 3xTF32) against fp32 FMA correlation forward, same inputs (why the FMA kernels are the default)
     for C, hh, ww in ((32, 96, 128), (128, 96, 128)):
         n = B * hh * ww

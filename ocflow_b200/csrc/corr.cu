@@ -74,17 +74,22 @@ constexpr int pad4mod8(int n) {
   return (r % 8 == 4) ? r : r + 4;
 }
 
-template <int D_, int PX_, int TXT_, int TH_, int CC_, int STAGES_>
+// NDY: vertical displacements handled by one CTA (one warp each).  d = 4: all 9.  d = 10 (FlowNetC family, 441 planes): 7 of the
+// 21, i.e. three CTAs per tile, each staging only the TH + 6 halo rows its displacements touch -- 21 warps x 84 accumulators would
+// not fit the register file.  MAXREG: register cap of the forward kernel (threads x registers must allow 2 CTAs per SM).
+template <int D_, int PX_, int TXT_, int TH_, int CC_, int STAGES_, int NDY_ = 2 * D_ + 1, int MAXREG_ = 96>
 struct CorrTile {
-  static constexpr int D = D_, PX = PX_, TXT = TXT_, TH = TH_, CC = CC_, STAGES = STAGES_;
+  static constexpr int D = D_, PX = PX_, TXT = TXT_, TH = TH_, CC = CC_, STAGES = STAGES_, NDY = NDY_, MAXREG = MAXREG_;
   static constexpr int ND = 2 * D + 1;
+  static constexpr int NGY = ND / NDY;          // CTAs (dy groups) per tile
+  static_assert(ND % NDY == 0, "the dy groups must tile the displacement range");
   static constexpr int TW = PX * TXT;
   static constexpr int F2W = TW + 2 * D;
-  static constexpr int F2H = TH + 2 * D;
+  static constexpr int F2H = TH + NDY - 1;      // halo rows of one dy group (== TH + 2 D when NDY == ND)
   static constexpr int S1 = pad4mod8(TW);
   static constexpr int S2 = pad4mod8(F2W);
   static constexpr int LANES = TXT * TH;  // pixel-threads per dy (one warp when == 32)
-  static constexpr int THREADS = LANES * ND;
+  static constexpr int THREADS = LANES * NDY;
   static constexpr int WIN = PX + 2 * D;  // f2 window per thread
   static constexpr int F1_STAGE = CC * TH * S1;    // floats per stage
   static constexpr int F2_STAGE = CC * F2H * S2;
@@ -157,35 +162,34 @@ __device__ __forceinline__ void consumer_bar_sync() {  // named barrier 1: the c
   asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
 }
 
+__device__ __forceinline__ void cp_async8(float* smem_dst, const float* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+
 // Asynchronously copies a [CC][ROWS][COLS] box of one batch item of a NCHW tensor (origin (yb, xb), may be negative
 // or past the edge; channels [c0, c0+CC) clipped to c_end) into shared memory with row stride S; everything outside
-// is zero-filled by the copy engine.  VEC: rows are 16-byte aligned in global memory (W % 4 == 0, xb % 4 == 0).
-template <int CC, int ROWS, int COLS, int S, int THREADS, bool VEC>
+// is zero-filled by the copy engine.  VW = floats per copy: 4 needs 16-byte aligned rows and box origin (W % 4 == 0, xb % 4 == 0),
+// 2 needs them 8-byte aligned (W % 2 == 0, xb % 2 == 0: the d = 10 halo, which starts at x0 - 10), 1 nothing.
+template <int CC, int ROWS, int COLS, int S, int THREADS, int VW>
 __device__ __forceinline__ void stage_box_async(float* __restrict__ dst, const float* __restrict__ src_b, int c0, int c_end,
                                                 int H, int W, int yb, int xb) {
-  if (VEC) {
-    constexpr int C4 = COLS / 4;
-    constexpr int ITEMS = CC * ROWS * C4;
+  static_assert(VW == 1 || VW == 2 || VW == 4, "copy width");
+  constexpr int CV = COLS / VW;
+  constexpr int ITEMS = CC * ROWS * CV;
+  static_assert(COLS % VW == 0, "box width must be a multiple of the copy width");
 #pragma unroll 4
-    for (int i = threadIdx.x; i < ITEMS; i += THREADS) {
-      const int row = i / C4, q = i - row * C4;
-      const int c = row / ROWS, r = row - c * ROWS;
-      const int gy = yb + r, gx = xb + q * 4, gc = c0 + c;
-      const bool ok = gc < c_end && gy >= 0 && gy < H && gx >= 0 && gx < W;
-      const float* src = ok ? src_b + ((size_t)gc * H + gy) * W + gx : src_b;
-      cp_async16(dst + (c * ROWS + r) * S + q * 4, src, ok);
-    }
-  } else {
-    constexpr int ITEMS = CC * ROWS * COLS;
-#pragma unroll 4
-    for (int i = threadIdx.x; i < ITEMS; i += THREADS) {
-      const int row = i / COLS, x = i - row * COLS;
-      const int c = row / ROWS, r = row - c * ROWS;
-      const int gy = yb + r, gx = xb + x, gc = c0 + c;
-      const bool ok = gc < c_end && gy >= 0 && gy < H && gx >= 0 && gx < W;
-      const float* src = ok ? src_b + ((size_t)gc * H + gy) * W + gx : src_b;
-      cp_async4(dst + (c * ROWS + r) * S + x, src, ok);
-    }
+  for (int i = threadIdx.x; i < ITEMS; i += THREADS) {
+    const int row = i / CV, q = i - row * CV;
+    const int c = row / ROWS, r = row - c * ROWS;
+    const int gy = yb + r, gx = xb + q * VW, gc = c0 + c;
+    const bool ok = gc < c_end && gy >= 0 && gy < H && gx >= 0 && gx < W;   // a VW-aligned group is entirely inside or outside the row
+    const float* src = ok ? src_b + ((size_t)gc * H + gy) * W + gx : src_b;
+    float* d = dst + (c * ROWS + r) * S + q * VW;
+    if (VW == 4) cp_async16(d, src, ok);
+    else if (VW == 2) cp_async8(d, src, ok);
+    else cp_async4(d, src, ok);
   }
 }
 
@@ -215,7 +219,7 @@ __device__ __forceinline__ ChunkRange chunk_range(int C, int CC, int ksplit, int
 // ---- forward ------------------------------------------------------------------------------------
 // grid (tiles_x, tiles_y, B * ksplit); when ksplit > 1 the launch carries cluster dims (1, 1, ksplit).
 template <class T, int STG>
-__global__ void __maxnreg__(96)
+__global__ void __maxnreg__(T::MAXREG)
 corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2, const float* __restrict__ f1,
                const float* __restrict__ f2, float* __restrict__ out, unsigned char* __restrict__ mask, int C, int H, int W,
                long long out_bstride, float inv_c, float slope, int ksplit) {
@@ -231,7 +235,9 @@ corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
   const int tx = lane % T::TXT, ty = lane / T::TXT;
   const int dyi = tid / T::LANES;
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-  const int b = blockIdx.z / ksplit, ks = blockIdx.z - b * ksplit;
+  // blockIdx.z = (b * NGY + dy group) * ksplit + channel slice
+  const int zz = blockIdx.z / ksplit, ks = blockIdx.z - zz * ksplit;
+  const int b = zz / T::NGY, dy0 = (zz - b * T::NGY) * T::NDY;
   const ChunkRange cr = chunk_range(C, CC, ksplit, ks);
   const int nchunks = cr.count;
 
@@ -303,11 +309,11 @@ corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
       const int c0 = (cr.begin + i) * CC;
       mbar_expect_tx(&full_bar[s], BYTES);
       tma_load_4d(st, &map1, &full_bar[s], x0, y0, c0, b);
-      tma_load_4d(st + T::F1_STAGE, &map2, &full_bar[s], x0 - D, y0 - D, c0, b);
+      tma_load_4d(st + T::F1_STAGE, &map2, &full_bar[s], x0 - D, y0 - D + dy0, c0, b);
     };
     if (tid == 0) {
 #pragma unroll
-      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ND); }
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], T::NDY); }
       mbar_fence_init();
 #pragma unroll
       for (int s = 0; s < STAGES; ++s)
@@ -332,8 +338,9 @@ corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
     auto issue = [&](int i) {
       float* st = smem + (i % STAGES) * STAGE;
       const int c0 = (cr.begin + i) * CC;
-      stage_box_async<CC, TH, TW, S1, T::THREADS, STG == STG_ASYNC16>(st, f1b, c0, C, H, W, y0, x0);
-      stage_box_async<CC, F2H, F2W, S2, T::THREADS, STG == STG_ASYNC16>(st + T::F1_STAGE, f2b, c0, C, H, W, y0 - D, x0 - D);
+      stage_box_async<CC, TH, TW, S1, T::THREADS, STG == STG_ASYNC16 ? 4 : 1>(st, f1b, c0, C, H, W, y0, x0);
+      // the halo starts at x0 - D: 16-byte copies need D % 4 == 0 (d = 10 stages its halo with 8-byte copies)
+      stage_box_async<CC, F2H, F2W, S2, T::THREADS, STG != STG_ASYNC16 ? 1 : (D % 4 == 0 ? 4 : 2)>(st + T::F1_STAGE, f2b, c0, C, H, W, y0 - D + dy0, x0 - D);
     };
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
@@ -355,7 +362,7 @@ corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
   if (ksplit == 1) {
     const int y = y0 + ty, xs = x0 + tx * PX;
     if (y >= H || xs >= W) return;
-    float* ob = out + (size_t)b * bstride + ((size_t)(dyi * ND) * H + y) * W + xs;
+    float* ob = out + (size_t)b * bstride + ((size_t)((dy0 + dyi) * ND) * H + y) * W + xs;
     const int Wb = (W + 7) >> 3;
 #pragma unroll
     for (int dx = 0; dx < ND; ++dx) {
@@ -367,7 +374,7 @@ corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
         mbyte |= (v > 0.f ? 1u : 0u) << p;
         r[p] = v > 0.f ? v : v * slope;
       }
-      if (mask != nullptr) mask[(((size_t)b * ND * ND + dyi * ND + dx) * H + y) * Wb + (xs >> 3)] = (unsigned char)mbyte;
+      if (mask != nullptr) mask[(((size_t)b * ND * ND + (dy0 + dyi) * ND + dx) * H + y) * Wb + (xs >> 3)] = (unsigned char)mbyte;
       float* o = ob + (size_t)dx * H * W;
       if (VEC) {  // W % 4 == 0 and 16B-aligned rows: each float4 is entirely inside or outside
 #pragma unroll
@@ -383,6 +390,9 @@ corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
   }
 
   // ---- channel-split: reduce the ksplit partial cost volumes of the cluster through DSMEM ----
+  if constexpr (T::NDY != T::ND) {
+    return;   // the dy-group tiles (d = 10) are never launched with a channel split
+  } else {
   cg::cluster_group cluster = cg::this_cluster();
   __syncthreads();  // every warp is done reading the staging ring; reuse it as the partial tile [ND*ND][TH][S1]
   float* part = smem;
@@ -448,6 +458,7 @@ corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
     }
   }
   cluster.sync();  // nobody may exit while a peer still reads its shared memory
+  }
 }
 
 // ---- forward, persistent (regular shapes, no channel split) -----------------------------------------
@@ -666,7 +677,7 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
   static_assert(CC % CR == 0, "CC must be a multiple of CR");
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES], g_bar, gdone_bar;
-  float* red = smem + STAGES * T::F2_STAGE;  // [ND][CR][TH][S1]
+  float* red = smem + STAGES * T::F2_STAGE;  // [NDY][CR][TH][S1]
   // TMA variant: the 81 coefficient planes of the tile are staged through shared memory first (one {GW, TH, ND} box per
   // dy-warp, GW == 12 mod 32 floats so the 128-bit reads are conflict-free); the area is then reused by the ring + red.
   constexpr int GW = T::S2, BOXG = ND * TH * GW;
@@ -676,7 +687,11 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
   const int tx = lane % T::TXT, ty = lane / T::TXT;
   const int dyi = tid / T::LANES;  // == ND for the TMA producer warp
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-  const int zz = blockIdx.z / ksplit, ks = blockIdx.z - zz * ksplit;
+  // blockIdx.z = ((b * nmodes + slot) * NGY + dy group) * ksplit + channel slice.  With several dy groups per tile (d = 10) every
+  // group adds its partial sum into the zero-filled output with vector reds; one group (d = 4) stores.
+  const int zz0 = blockIdx.z / ksplit, ks = blockIdx.z - zz0 * ksplit;
+  const int zz = zz0 / T::NGY, dy0 = (zz0 - zz * T::NGY) * T::NDY;
+  static_assert(T::NGY == 1 || STG != STG_TMA, "the TMA-staged backward handles all displacements in one CTA");
   const int b = zz / nmodes;
   const int mode = first_mode + (zz - b * nmodes);
   const ChunkRange cr = chunk_range(C, CC, ksplit, ks);
@@ -853,8 +868,8 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
   const float* fo = (mode == 0 ? f2 + (size_t)b * (f2_bstride ? (size_t)f2_bstride : (size_t)C * H * W)
                                : f1 + (size_t)b * (f1_bstride ? (size_t)f1_bstride : (size_t)C * H * W));
   auto issue = [&](int i) {
-    stage_box_async<CC, F2H, F2W, S2, T::THREADS, STG == STG_ASYNC16>(smem + (i % STAGES) * T::F2_STAGE, fo, (cr.begin + i) * CC, C, H, W,
-                                                                      y0 - D, x0 - D);
+    stage_box_async<CC, F2H, F2W, S2, T::THREADS, STG != STG_ASYNC16 ? 1 : (D % 4 == 0 ? 4 : 2)>(smem + (i % STAGES) * T::F2_STAGE, fo, (cr.begin + i) * CC,
+                                                                                                  C, H, W, y0 - D + dy0, x0 - D);
   };
   if constexpr (!TMA) {
 #pragma unroll
@@ -866,8 +881,9 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
 #pragma unroll
     for (int dx = 0; dx < ND; ++dx) {
       // mode 0: plane k(dy,dx) at (y, x) ; mode 1: plane k(-dy,-dx) at (y+dy, x+dx)
-      const int k = mode == 0 ? dyi * ND + dx : (2 * D - dyi) * ND + (2 * D - dx);
-      const int sy = mode == 0 ? y : y + dyi - D;
+      const int dyg = dy0 + dyi;   // this warp's vertical displacement index in 0 .. ND-1
+      const int k = mode == 0 ? dyg * ND + dx : (2 * D - dyg) * ND + (2 * D - dx);
+      const int sy = mode == 0 ? y : y + dyg - D;
       const int sx0 = mode == 0 ? xs : xs + dx - D;
       const size_t off = gb + ((size_t)k * H + sy) * W;
 #pragma unroll
@@ -928,14 +944,22 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
         const int c = row / TH, ry = row - c * TH;
         float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < ND; ++k) {
+        for (int k = 0; k < T::NDY; ++k) {
           const float4 v = *reinterpret_cast<const float4*>(red + ((k * CR + c) * TH + ry) * S1 + x4 * 4);
           sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
         }
         const int ch = c0 + r0 + c, y = y0 + ry, x = x0 + x4 * 4;
         if (ch < C && y < H && x < W) {
           float* o = dout + ((size_t)ch * H + y) * W + x;
-          if (VEC) {
+          if (T::NGY > 1) {   // partial sum of one dy group: accumulate (the entry point zero-fills the output)
+            if (VEC) red_add_v4(o, sum.x * inv_c, sum.y * inv_c, sum.z * inv_c, sum.w * inv_c);
+            else {
+              atomicAdd(o, sum.x * inv_c);
+              if (x + 1 < W) atomicAdd(o + 1, sum.y * inv_c);
+              if (x + 2 < W) atomicAdd(o + 2, sum.z * inv_c);
+              if (x + 3 < W) atomicAdd(o + 3, sum.w * inv_c);
+            }
+          } else if (VEC) {
             *reinterpret_cast<float4*>(o) = make_float4(sum.x * inv_c, sum.y * inv_c, sum.z * inv_c, sum.w * inv_c);
           } else {
             o[0] = sum.x * inv_c;
@@ -997,6 +1021,8 @@ corr_bwd_generic(const float* __restrict__ g, const float* __restrict__ oact, co
 }
 
 using Tile4 = CorrTile<4, 8, 4, 8, 8, 3>;
+// d = 10: 4 x 32 pixel tile, thread = 4 pixels x 21 horizontal displacements (84 accumulators), 7 dy-warps per CTA, 3 CTAs per tile
+using Tile10 = CorrTile<10, 4, 8, 4, 8, 3, 7, 128>;
 #ifndef OCF_FWD_STAGES
 #define OCF_FWD_STAGES 6
 #endif
@@ -1187,6 +1213,25 @@ static int corr_fwd_impl(const float* f1, long long f1_bstride, const float* f2,
       if (int e = set_smem(kernel, smem)) return e;
       if (int e = launch_kernel(kernel, grid, T::THREADS, smem, s, ks, m1, m2, f1, f2, out, mask_out, C, H, W, out_bstride, inv_c, leaky_slope, ks)) return e;
     }
+  } else if (d == 10 && norm == nullptr && f1_bstride == 0) {
+    // FlowNetC family (flow_net_c.py:22-25, flow_occ_net_c.py:26, occlusion_net_c.py:24): 21 x 21 = 441 planes
+    using T = Tile10;
+    const size_t smem = sizeof(float) * T::STAGES * (T::F1_STAGE + T::F2_STAGE);
+    const int gx = (W + T::TW - 1) / T::TW, gy = (H + T::TH - 1) / T::TH;
+    OCF_REQUIRE((long long)B * T::NGY <= 65535, OCF_EUNSUPPORTED);
+    dim3 grid(gx, gy, B * T::NGY);
+    const bool vec = (W % 4 == 0) && ocf_aligned16(f1) && ocf_aligned16(f2) && ocf_aligned16(out) && (out_bstride % 4 == 0);
+    CUtensorMap m1, m2;
+    memset(&m1, 0, sizeof(m1));
+    memset(&m2, 0, sizeof(m2));
+    // The TMA-staged instantiation of this tile FAULTS on B200 ("illegal instruction" at the first box; the d = 4 instantiation of the
+    // same kernel is fine and the cp.async instantiations of this tile are correct), cause not found yet: it stays behind a
+    // developer knob and d = 10 is staged with 16-byte (f1 tile) and 8-byte (halo, which starts at x0 - 10) cp.async copies.
+    static const int use_tma = []() { const char* e = getenv("OCF_CORR10_TMA"); return e ? atoi(e) : 0; }();
+    const bool tma = vec && use_tma && make_map(&m1, f1, B, C, H, W, T::S1, T::TH, T::CC) && make_map(&m2, f2, B, C, H, W, T::S2, T::F2H, T::CC);
+    auto kernel = tma ? corr_fwd_tiled<T, STG_TMA> : (vec ? corr_fwd_tiled<T, STG_ASYNC16> : corr_fwd_tiled<T, STG_ASYNC4>);
+    if (int e = set_smem(kernel, smem)) return e;
+    if (int e = launch_kernel(kernel, grid, T::THREADS, smem, s, 1, m1, m2, f1, f2, out, (unsigned char*)nullptr, C, H, W, out_bstride, inv_c, leaky_slope, 1)) return e;
   } else {
     OCF_REQUIRE(f1_bstride == 0, OCF_EUNSUPPORTED);
     dim3 grid((H * W + 127) / 128, (unsigned)nd, B);
@@ -1266,6 +1311,27 @@ int ocf_corr_bwd_impl(const float* grad_out, const float* out_act, const float* 
       if (int e = launch_kernel(kernel, grid, T::THREADS, smem, s, 1, m1, m2, mg, grad_out, out_act, mask, f1, f2, df1, df2, C, H, W, g_bstride,
                                 act_bstride, inv_c, leaky_slope, nmodes, first, ks, f1_bstride, f2_bstride)) return e;
     }
+  } else if (d == 10 && f1_bstride == 0 && f2_bstride == 0) {
+    // FlowNetC family: three dy-group CTAs per tile and mode, partial sums accumulated with vector reds into the zeroed outputs
+    using T = Tile10;
+    const size_t smem = sizeof(float) * (T::STAGES * T::F2_STAGE + T::NDY * BWD_CR * T::TH * T::S1);
+    const int nmodes = (df1 != nullptr && df2 != nullptr) ? 2 : 1;
+    const int first = df1 != nullptr ? 0 : 1;
+    const int gx = (W + T::TW - 1) / T::TW, gy = (H + T::TH - 1) / T::TH;
+    OCF_REQUIRE((long long)B * nmodes * T::NGY <= 65535, OCF_EUNSUPPORTED);
+    dim3 grid(gx, gy, B * nmodes * T::NGY);
+    const bool vec = (W % 4 == 0) && ocf_aligned16(f1) && ocf_aligned16(f2) && (df1 == nullptr || ocf_aligned16(df1)) && (df2 == nullptr || ocf_aligned16(df2));
+    cudaError_t e;
+    if (df1 != nullptr && (e = cudaMemsetAsync(df1, 0, sizeof(float) * (size_t)B * C * H * W, s)) != cudaSuccess) return (int)e;
+    if (df2 != nullptr && (e = cudaMemsetAsync(df2, 0, sizeof(float) * (size_t)B * C * H * W, s)) != cudaSuccess) return (int)e;
+    CUtensorMap m1, m2, mg;
+    memset(&m1, 0, sizeof(m1));
+    memset(&m2, 0, sizeof(m2));
+    memset(&mg, 0, sizeof(mg));
+    auto kernel = vec ? corr_bwd_tiled<T, BWD_CR, STG_ASYNC16> : corr_bwd_tiled<T, BWD_CR, STG_ASYNC4>;
+    if (int er = set_smem(kernel, smem)) return er;
+    if (int er = launch_kernel(kernel, grid, T::THREADS, smem, s, 1, m1, m2, mg, grad_out, out_act, mask, f1, f2, df1, df2, C, H, W, g_bstride,
+                               act_bstride, inv_c, leaky_slope, nmodes, first, 1, f1_bstride, f2_bstride)) return er;
   } else {
     OCF_REQUIRE(f1_bstride == 0 && f2_bstride == 0, OCF_EUNSUPPORTED);
     dim3 grid((H * W + 127) / 128, C, B);

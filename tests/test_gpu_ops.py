@@ -302,3 +302,29 @@ def test_corr_persistent_kernels_match_oracle(B, C, H, W, slope):
     assert only1[2] is None and only2[1] is None
     assert_close(only1[1], want[1], TOL, "d f1 alone")
     assert_close(only2[2], want[2], TOL, "d f2 alone")
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 32, 24, 32), (1, 20, 17, 23), (1, 64, 48, 64), (2, 7, 5, 9), (1, 256, 12, 16), (3, 16, 30, 44)])
+@pytest.mark.parametrize("slope", [1.0, 0.1])
+def test_corr_d10_tiled_forward_matches_oracle(B, C, H, W, slope):
+    """max_displacement = 10 (441 planes, the FlowNetC-family call sites flow_net_c.py:22-25 / flow_occ_net_c.py:26 /
+    occlusion_net_c.py:24): the tiled forward (three dy-group CTAs per tile; TMA, 16-byte cp.async and ragged 4-byte staging)
+    and the tiled backward (partial sums of the three dy groups accumulated with vector reds) against the fp64 oracle."""
+    from ocflow_b200 import ops
+
+    g = torch.Generator().manual_seed(B * 131 + C * 17 + H * 5 + W)
+    f1 = torch.randn(B, C, H, W, generator=g)
+    f2 = torch.randn(B, C, H, W, generator=g) + 0.2
+    a, b = f1.double().requires_grad_(True), f2.double().requires_grad_(True)
+    ref = O.cost_volume(a, b, 10)
+    if slope != 1.0:
+        ref = torch.nn.functional.leaky_relu(ref, slope)
+    cot = torch.randn(ref.shape, generator=g)
+    ga, gb = torch.autograd.grad((ref * cot.double()).sum(), (a, b))
+    x1, x2 = f1.cuda().requires_grad_(True), f2.cuda().requires_grad_(True)
+    out = ops.cost_volume(x1, x2, 10, leaky_slope=slope)
+    assert out.shape == (B, 441, H, W)
+    assert_close(out, ref, TOL, "corr d=10 slope=%g" % slope)
+    g1, g2 = torch.autograd.grad((out * cot.cuda()).sum(), (x1, x2))
+    assert_close(g1, ga, TOL, "corr d=10 grad f1")
+    assert_close(g2, gb, TOL, "corr d=10 grad f2")
