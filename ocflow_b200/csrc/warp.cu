@@ -360,7 +360,7 @@ extern "C" int ocf_warp_fwd(const float* img, const float* flow, const float* oc
   OCF_REQUIRE((flags & ~3) == 0, OCF_EUNSUPPORTED);
   const int HW = H * W;
   const int kcb = warp_cb(true);
-  const int cb = (C < 4 || kcb == 1) ? 1 : ((C < 8 || kcb == 4) ? 4 : 8);
+  const int cb = (C < 2 || kcb == 1) ? 1 : ((C < 8 || kcb == 4) ? 4 : 8);   // C = 3 (images): one batch of 4, the 4th load repeats channel 2
   const int slab = pick_slab(C, HW, B, cb);
   const int nslabs = (C + slab - 1) / slab;
   OCF_REQUIRE(nslabs <= 65535, OCF_EUNSUPPORTED);
@@ -384,7 +384,7 @@ extern "C" int ocf_warp_bwd(const float* grad_out, const float* img, const float
   cudaStream_t s = ocf_cast_stream(stream);
   const int HW = H * W;
   const int kcb = warp_cb(false);
-  const int cb = (C < 4 || kcb == 1) ? 1 : ((C < 8 || kcb == 4) ? 4 : 8);
+  const int cb = (C < 2 || kcb == 1) ? 1 : ((C < 8 || kcb == 4) ? 4 : 8);   // C = 3 (images): one batch of 4, the 4th load repeats channel 2
   const int slab = pick_slab(C, HW, B, cb);
   const int nslabs = (C + slab - 1) / slab;
   OCF_REQUIRE(nslabs <= 65535, OCF_EUNSUPPORTED);
