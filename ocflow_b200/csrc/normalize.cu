@@ -25,6 +25,7 @@ namespace {
 
 constexpr int NT = 256;
 constexpr int MAX_T = 8;
+constexpr int UB = 8;   // float4 groups per thread and tensor in the vectorised kernels
 
 struct PtrPack {
   const float* in[MAX_T];
@@ -110,31 +111,26 @@ group_sums_kernel(PtrPack pk, int B, int G, size_t glen, float* __restrict__ ws,
   const float pivot = SECOND ? 0.f : __ldg(x);   // forward: sums of (x - pivot), see finalize_fwd
   float acc[2] = {0.f, 0.f};
   if (VEC) {
+    // a CTA owns NT * UB consecutive float4 groups; a thread's UB loads (2 UB in the backward) are all issued before the
+    // first use -- the one-load-per-iteration form was latency bound (ncu: long_scoreboard, SMs idle half of the time)
     const size_t n4 = glen / 4;
-    const size_t per = (n4 + gridDim.x - 1) / gridDim.x;
-    const size_t lo = (size_t)blockIdx.x * per, hi = min(n4, lo + per);
-    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;  // two independent chains per sum
-    size_t i = lo + threadIdx.x;
-    for (; i + NT < hi; i += 2 * NT) {
-      float4 u = ocf_ldg_stream4(x + 4 * i), v = ocf_ldg_stream4(x + 4 * (i + NT));
-      if (!SECOND) {
-        u.x -= pivot; u.y -= pivot; u.z -= pivot; u.w -= pivot;
-        v.x -= pivot; v.y -= pivot; v.z -= pivot; v.w -= pivot;
-      }
-      float4 p = u, q = v;
-      if (SECOND) { p = ocf_ldg_stream4(w + 4 * i); q = ocf_ldg_stream4(w + 4 * (i + NT)); }
-      a0 += (u.x + u.y) + (u.z + u.w);
-      a1 += (v.x + v.y) + (v.z + v.w);
-      b0 = fmaf(u.x, p.x, fmaf(u.y, p.y, fmaf(u.z, p.z, fmaf(u.w, p.w, b0))));
-      b1 = fmaf(v.x, q.x, fmaf(v.y, q.y, fmaf(v.z, q.z, fmaf(v.w, q.w, b1))));
+    const size_t base = (size_t)blockIdx.x * (NT * UB) + threadIdx.x;
+    float4 u[UB], p[UB];
+#pragma unroll
+    for (int k = 0; k < UB; ++k) {
+      const size_t i = base + (size_t)k * NT;
+      u[k] = i < n4 ? ocf_ldg_stream4(x + 4 * i) : make_float4(pivot, pivot, pivot, pivot);
+      if (SECOND) p[k] = i < n4 ? ocf_ldg_stream4(w + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (i < hi) {
-      float4 u = ocf_ldg_stream4(x + 4 * i);
-      if (!SECOND) { u.x -= pivot; u.y -= pivot; u.z -= pivot; u.w -= pivot; }
-      float4 p = u;
-      if (SECOND) p = ocf_ldg_stream4(w + 4 * i);
-      a0 += (u.x + u.y) + (u.z + u.w);
-      b0 = fmaf(u.x, p.x, fmaf(u.y, p.y, fmaf(u.z, p.z, fmaf(u.w, p.w, b0))));
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;  // two independent chains per sum
+#pragma unroll
+    for (int k = 0; k < UB; ++k) {
+      float4 v = u[k];
+      if (!SECOND) { v.x -= pivot; v.y -= pivot; v.z -= pivot; v.w -= pivot; }
+      else if (base + (size_t)k * NT >= n4) v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 q = SECOND ? p[k] : v;
+      if (k & 1) { a1 += (v.x + v.y) + (v.z + v.w); b1 = fmaf(v.x, q.x, fmaf(v.y, q.y, fmaf(v.z, q.z, fmaf(v.w, q.w, b1)))); }
+      else { a0 += (v.x + v.y) + (v.z + v.w); b0 = fmaf(v.x, q.x, fmaf(v.y, q.y, fmaf(v.z, q.z, fmaf(v.w, q.w, b0)))); }
     }
     acc[0] = a0 + a1;
     acc[1] = b0 + b1;
@@ -175,10 +171,21 @@ norm_apply_kernel(PtrPack pk, int B, int G, size_t glen, const float* __restrict
   const float m = app[2 * gidx], r = app[2 * gidx + 1];
   if (vec) {
     const size_t n4 = glen / 4;
-    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < n4; i += (size_t)gridDim.x * NT) {
-      float4 v = reinterpret_cast<const float4*>(x)[i];
-      v.x = (v.x - m) * r; v.y = (v.y - m) * r; v.z = (v.z - m) * r; v.w = (v.w - m) * r;
-      reinterpret_cast<float4*>(y)[i] = v;
+    const size_t base = (size_t)blockIdx.x * (NT * UB) + threadIdx.x;
+    float4 v[UB];
+#pragma unroll
+    for (int k = 0; k < UB; ++k) {
+      const size_t i = base + (size_t)k * NT;
+      if (i < n4) v[k] = ocf_ldg_stream4(x + 4 * i);
+    }
+#pragma unroll
+    for (int k = 0; k < UB; ++k) {
+      const size_t i = base + (size_t)k * NT;
+      if (i < n4) {
+        float4 o = v[k];
+        o.x = (o.x - m) * r; o.y = (o.y - m) * r; o.z = (o.z - m) * r; o.w = (o.w - m) * r;
+        reinterpret_cast<float4*>(y)[i] = o;
+      }
     }
   } else {
     for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < glen; i += (size_t)gridDim.x * NT) y[i] = (x[i] - m) * r;
@@ -198,12 +205,22 @@ norm_bwd_apply_kernel(PtrPack pk, int B, int G, size_t glen, const float* __rest
   const float r = co[0], A = co[1], Bc = co[2];
   if (vec) {
     const size_t n4 = glen / 4;
-    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < n4; i += (size_t)gridDim.x * NT) {
-      const float4 gv = ocf_ldg_stream4(g + 4 * i), xv = ocf_ldg_stream4(x + 4 * i);
-      float4 o;
-      o.x = fmaf(gv.x, r, fmaf(Bc, xv.x - mu, A)); o.y = fmaf(gv.y, r, fmaf(Bc, xv.y - mu, A));
-      o.z = fmaf(gv.z, r, fmaf(Bc, xv.z - mu, A)); o.w = fmaf(gv.w, r, fmaf(Bc, xv.w - mu, A));
-      reinterpret_cast<float4*>(dx)[i] = o;
+    const size_t base = (size_t)blockIdx.x * (NT * UB) + threadIdx.x;
+    float4 gv[UB], xv[UB];
+#pragma unroll
+    for (int k = 0; k < UB; ++k) {
+      const size_t i = base + (size_t)k * NT;
+      if (i < n4) { gv[k] = ocf_ldg_stream4(g + 4 * i); xv[k] = ocf_ldg_stream4(x + 4 * i); }
+    }
+#pragma unroll
+    for (int k = 0; k < UB; ++k) {
+      const size_t i = base + (size_t)k * NT;
+      if (i < n4) {
+        float4 o;
+        o.x = fmaf(gv[k].x, r, fmaf(Bc, xv[k].x - mu, A)); o.y = fmaf(gv[k].y, r, fmaf(Bc, xv[k].y - mu, A));
+        o.z = fmaf(gv[k].z, r, fmaf(Bc, xv[k].z - mu, A)); o.w = fmaf(gv[k].w, r, fmaf(Bc, xv[k].w - mu, A));
+        reinterpret_cast<float4*>(dx)[i] = o;
+      }
     }
   } else {
     for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < glen; i += (size_t)gridDim.x * NT)
@@ -211,8 +228,13 @@ norm_bwd_apply_kernel(PtrPack pk, int B, int G, size_t glen, const float* __rest
   }
 }
 
-int chunks_for(size_t glen, int NG) {
-  // aim at ~4 CTAs per SM overall, each with at least 2048 elements
+// vectorised kernels: a CTA covers NT * UB float4 groups ; scalar fallbacks: ~4 CTAs per SM overall, >= 2048 elements each
+int chunks_for(size_t glen, int NG, bool vec) {
+  if (vec) {
+    const size_t n4 = glen / 4;
+    long long c = (long long)((n4 + (size_t)NT * UB - 1) / ((size_t)NT * UB));
+    return (int)(c < 1 ? 1 : c);
+  }
   long long want = (4LL * OCF_SM_COUNT + NG - 1) / NG;
   long long maxc = (long long)((glen + 2047) / 2048);
   if (want > maxc) want = maxc;
@@ -248,7 +270,7 @@ extern "C" int ocf_normalize_stats(const float* const* xs, int T, int B, int C, 
   unsigned* ticket = reinterpret_cast<unsigned*>(stats + 8 * (size_t)NG);
   cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(float) * (8 * (size_t)NG + 2), s);  // fp64 sums and the ticket in one go
   if (e != cudaSuccess) return (int)e;
-  const int chunks = chunks_for(glen, NG);
+  const int chunks = chunks_for(glen, NG, vec);
   if (vec) group_sums_kernel<false, true><<<dim3(chunks, NG), NT, 0, s>>>(pk, B, G, glen, stats, ticket, nullptr, NG, flags);
   else group_sums_kernel<false, false><<<dim3(chunks, NG), NT, 0, s>>>(pk, B, G, glen, stats, ticket, nullptr, NG, flags);
   return ocf_launch_status();
@@ -269,7 +291,7 @@ extern "C" int ocf_normalize_fwd(const float* const* xs, float* const* ys, int T
   const size_t glen = (size_t)(G == 1 ? C : 1) * H * W;
   const int NG = T * B * G;
   vec = vec && (glen % 4 == 0);
-  norm_apply_kernel<<<dim3(chunks_for(glen, NG), NG), NT, 0, ocf_cast_stream(stream)>>>(pk, B, G, glen, stats + 6 * (size_t)NG, vec);
+  norm_apply_kernel<<<dim3(chunks_for(glen, NG, vec), NG), NT, 0, ocf_cast_stream(stream)>>>(pk, B, G, glen, stats + 6 * (size_t)NG, vec);
   return ocf_launch_status();
 }
 
@@ -295,7 +317,7 @@ extern "C" int ocf_normalize_apply(const float* const* xs, float* const* ys, con
   OCF_REQUIRE(NGll <= 65535, OCF_EUNSUPPORTED);
   const int NG = (int)NGll;
   vec = vec && (glen % 4 == 0);
-  norm_apply_kernel<<<dim3(chunks_for(glen, NG), NG), NT, 0, ocf_cast_stream(stream)>>>(pk, B, G, glen, stats + 6 * (size_t)NG, vec);
+  norm_apply_kernel<<<dim3(chunks_for(glen, NG, vec), NG), NT, 0, ocf_cast_stream(stream)>>>(pk, B, G, glen, stats + 6 * (size_t)NG, vec);
   return ocf_launch_status();
 }
 
@@ -323,7 +345,7 @@ extern "C" int ocf_normalize_bwd(const float* const* grad_ys, const float* const
   unsigned* ticket = reinterpret_cast<unsigned*>(red + 7 * (size_t)NG);
   cudaError_t e = cudaMemsetAsync(red, 0, sizeof(float) * (8 * (size_t)NG), s);  // fp64 sums and the ticket in one go
   if (e != cudaSuccess) return (int)e;
-  const int chunks = chunks_for(glen, NG);
+  const int chunks = chunks_for(glen, NG, vec);
   if (vec) group_sums_kernel<true, true><<<dim3(chunks, NG), NT, 0, s>>>(pk, B, G, glen, red, ticket, stats, NG, flags);
   else group_sums_kernel<true, false><<<dim3(chunks, NG), NT, 0, s>>>(pk, B, G, glen, red, ticket, stats, NG, flags);
   if (int st = ocf_launch_status()) return st;
