@@ -280,6 +280,10 @@ int ocf_flow_metrics(const float* gt, const float* pred, const float* mask, doub
  * ------------------------------------------------------------------------------------------- */
 int ocf_pack_pairs(const unsigned char* img1, const unsigned char* img2, const float* flow_hw2, float* imgs, float* flow,
                    int B, int H0, int W0, int H, int W, int y0, int x0, ocf_stream_t stream);
+/* FlyingChairs2 ground-truth occlusion mask (models/data/datasets.py:660-669): occ_u8 [B,H0,W0] uint8 as decoded -> crop ->
+ * occ [B,1,H,W] fp32 in {0, 1} (occ[occ > 0.5] = 1 ; occ[occ != 1] = 0 on the float copy of the decoded values). */
+int ocf_pack_occ(const unsigned char* occ_u8, float* occ, int B, int H0, int W0, int H, int W, int y0, int x0,
+                 ocf_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Host-buffer convenience entry points (HOST pointers; allocate, copy in, run, copy out, free,

@@ -48,6 +48,7 @@ SIGNATURES = {
     "ocf_census_fwd": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_s],
     "ocf_census_bwd": [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_s],
     "ocf_flow_metrics": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_s],
+    "ocf_pack_occ": [c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_s],
     "ocf_pack_pairs": [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_s],
     "ocf_host_corr_fwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i],
     "ocf_host_warp_fwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i],
@@ -92,7 +93,7 @@ KERNELS_PER_CALL = {
     "ocf_corr_fwd": 1, "ocf_corr_bwd": 1, "ocf_normalize_stats": 1, "ocf_normalize_apply": 1, "ocf_corr_fwd_strided": 1, "ocf_level_corr_fwd": 1, "ocf_level_corr_bwd": 1, "ocf_normalize_fwd": 2, "ocf_normalize_bwd": 2, "ocf_warp_fwd": 1, "ocf_resize_bilinear_fwd": 1, "ocf_resize_bilinear_bwd": 1,
     "ocf_warp_bwd": 1, "ocf_range_map": 1, "ocf_flow_to_warp": 1, "ocf_robust_l1_fwd": 1, "ocf_robust_l1_bwd": 1,
     "ocf_photometric_fwd": 1, "ocf_photometric_bwd": 1, "ocf_smooth_fwd": 1, "ocf_smooth_bwd": 1, "ocf_gradient": 1,
-    "ocf_occ_photo_fused": 1, "ocf_pair_loss": 1, "ocf_ssim_fwd": 1, "ocf_ssim_bwd": 1, "ocf_census_fwd": 1, "ocf_census_bwd": 1, "ocf_flow_metrics": 1, "ocf_pack_pairs": 1,
+    "ocf_occ_photo_fused": 1, "ocf_pair_loss": 1, "ocf_ssim_fwd": 1, "ocf_ssim_bwd": 1, "ocf_census_fwd": 1, "ocf_census_bwd": 1, "ocf_flow_metrics": 1, "ocf_pack_pairs": 1, "ocf_pack_occ": 1,
 }
 
 

@@ -927,6 +927,9 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
         }
 #pragma unroll
         for (int p = 0; p < PX; ++p) part[p] = 0.f;
+        // (Measured: the same loop as packed fma.rn.f32x2 over pixel pairs -- aligned window pairs for even dx, a shifted copy of
+        // the window for odd dx -- is 8-15 % SLOWER (L2 level 65.6 vs 60.4 us, C = 128: 208 vs 181 us): the 15 register-pair
+        // packs per channel cost more issue slots than the 36 saved FMAs.)
 #pragma unroll
         for (int dx = 0; dx < ND; ++dx)
 #pragma unroll
@@ -977,6 +980,201 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
     }
   }
   if constexpr (!TMA) cp_async_wait<0>();
+}
+
+// ---- backward, channel-split persistent form (d = 4, TMA, sign bitmask or no activation) ------------------------------
+// The tiled backward above gives every vertical displacement its own warp and reduces the nine partial sums through
+// shared memory with two block barriers per 4 channels.  Here a warp owns a GROUP OF CHANNELS instead and walks all nine
+// dy itself, so nothing is reduced across warps and the main loop has no barrier at all:
+//   * one persistent CTA per SM walks the work items (tile, mode);
+//   * the 81 coefficient planes of the item are TMA-staged once into shared memory (114 KB, resident for the whole item), the
+//     LeakyReLU sign mask is folded into the staged copy by a cooperative pass (one block barrier per item);
+//   * compute warp w takes the 8-channel groups w, w + NW, ...: per dy it lifts its 72 coefficients (9 dx x 8 pixels) from
+//     shared memory ONCE and applies them to the 8 channels of the group (8 x 72 FMAs against 18 + 32 LDS.128), accumulating
+//     8 x 8 outputs in registers; the feature boxes of a group arrive through a TMA ring whose stages are per warp;
+//   * outputs go straight from registers to global memory (128-bit stores).
+template <class T, int NW, int RING>
+__global__ void __launch_bounds__((NW + 1) * 32, 1)
+corr_bwd_cs(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap mapg,
+            const unsigned char* __restrict__ mask, float* __restrict__ df1, float* __restrict__ df2, int C, int H, int W, float inv_c,
+            float slope, int nmodes, int first_mode, int tiles_x, int tiles_y, int nitems) {
+  constexpr int D = T::D, PX = T::PX, ND = T::ND, TH = T::TH, TW = T::TW, CC = T::CC;
+  constexpr int S2 = T::S2, F2H = T::F2H, WIN = T::WIN;
+  constexpr int GW = T::S2, BOXG = ND * TH * GW;          // one {GW, TH, ND} box per dy
+  constexpr int GFLOATS = ND * BOXG;
+  static_assert(ND == 9 && PX == 8 && CC == 8, "d = 4 tile");
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) unsigned long long full_bar[RING], empty_bar[RING], g_bar, gfree_bar;
+  float* gs = smem;                      // [dy][dx][TH][GW]
+  float* ring = smem + GFLOATS;          // RING x F2_STAGE
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tx = lane % T::TXT, ty = lane / T::TXT;
+  const int ngroups = (C + CC - 1) / CC;
+  const int nit = ((int)blockIdx.x < nitems) ? (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < RING; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&g_bar, 1);
+    mbar_init(&gfree_bar, NW);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  auto item_coord = [&](int it, int& b, int& mode, int& x0, int& y0) {
+    const int item = (int)blockIdx.x + it * (int)gridDim.x;
+    const int tile = item / nmodes;
+    mode = first_mode + (item - tile * nmodes);
+    const int txi = tile % tiles_x, r = tile / tiles_x;
+    x0 = txi * TW; y0 = (r % tiles_y) * TH; b = r / tiles_y;
+  };
+
+  if (warp == NW) {
+    // =========================== producer ===========================
+    if (lane == 0) {
+      int n = 0;   // flat feature-stage counter
+      for (int it = 0; it < nit; ++it) {
+        int b, mode, x0, y0;
+        item_coord(it, b, mode, x0, y0);
+        if (it > 0) mbar_wait(&gfree_bar, (it - 1) & 1);   // every compute warp is done with the previous item's coefficients
+        mbar_expect_tx(&g_bar, (unsigned)(sizeof(float) * GFLOATS));
+        for (int w = 0; w < ND; ++w) {
+          // mode 0 -> planes dy*ND.. at (y0, x0) ; mode 1 -> planes (2D-dy)*ND.. at (y0+dy-D, x0-D)
+          const int plane0 = mode == 0 ? w * ND : (2 * D - w) * ND;
+          tma_load_4d(gs + w * BOXG, &mapg, &g_bar, mode == 0 ? x0 : x0 - D, mode == 0 ? y0 : y0 + w - D, plane0, b);
+        }
+        const CUtensorMap* map = mode == 0 ? &map2 : &map1;  // the OTHER feature
+        for (int gi = 0; gi < ngroups; ++gi, ++n) {
+          const int s = n % RING;
+          if (n >= RING) mbar_wait(&empty_bar[s], ((n / RING) - 1) & 1);
+          mbar_expect_tx(&full_bar[s], (unsigned)(sizeof(float) * T::F2_STAGE));
+          tma_load_4d(ring + s * T::F2_STAGE, map, &full_bar[s], x0 - D, y0 - D, gi * CC, b);
+        }
+      }
+    }
+    return;
+  }
+
+  // =========================== compute warps ===========================
+  for (int it = 0; it < nit; ++it) {
+    int b, mode, x0, y0;
+    item_coord(it, b, mode, x0, y0);
+    // LeakyReLU derivative: element (dy, dx, r, x) of the staged boxes is plane k at (sy, sx).  The sign bytes of this thread's
+    // NE float4 groups are requested BEFORE the wait for the coefficient boxes (one L2 round trip, overlapped with the TMA
+    // transfer); afterwards the staged copy is scaled in place (one block barrier per item).
+    constexpr int G4 = GW / 4, NE = (ND * ND * TH * G4 + NW * 32 - 1) / (NW * 32);
+    unsigned mword[(NE + 3) / 4];   // 4 sign bytes per register
+#pragma unroll
+    for (int j = 0; j < (NE + 3) / 4; ++j) mword[j] = 0u;
+    if (mask != nullptr) {
+      const int Wb = (W + 7) >> 3;
+      const unsigned char* mp = mask + (size_t)b * ND * ND * H * Wb;
+#pragma unroll
+      for (int j = 0; j < NE; ++j) {
+        const int e = tid + j * NW * 32;
+        const int x4 = e % G4, r3 = e / G4;
+        const int r = r3 % TH, pl = min(r3 / TH, ND * ND - 1);   // pl = dy * ND + dx (box order)
+        const int dy = pl / ND, dxb = pl - dy * ND;
+        const int k = mode == 0 ? pl : (2 * D - dy) * ND + dxb;
+        const int sy = min(max(mode == 0 ? y0 + r : y0 + dy - D + r, 0), H - 1);
+        const int sx = min(max((mode == 0 ? x0 : x0 - D) + 4 * x4, 0), W - 4);   // clamped: out-of-image coefficients are zero anyway
+        mword[j >> 2] |= (unsigned)__ldg(mp + ((size_t)k * H + sy) * Wb + (sx >> 3)) << (8 * (j & 3));
+      }
+    }
+    mbar_wait(&g_bar, it & 1);
+    if (mask != nullptr) {
+#pragma unroll
+      for (int j = 0; j < NE; ++j) {
+        const int e = tid + j * NW * 32;
+        if (e < ND * ND * TH * G4) {
+          const int x4 = e % G4;
+          const int sx = min(max((mode == 0 ? x0 : x0 - D) + 4 * x4, 0), W - 4);
+          const unsigned bits = ((mword[j >> 2] >> (8 * (j & 3))) & 0xffu) >> (sx & 7);
+          float4* gp4 = reinterpret_cast<float4*>(gs + 4 * (size_t)e);   // e enumerates the float4 groups of the boxes in memory order
+          float4 v = *gp4;
+          if (!(bits & 1u)) v.x *= slope;
+          if (!(bits & 2u)) v.y *= slope;
+          if (!(bits & 4u)) v.z *= slope;
+          if (!(bits & 8u)) v.w *= slope;
+          *gp4 = v;
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+    }
+    float* dout = (mode == 0 ? df1 : df2) + (size_t)b * C * H * W;
+    const int y = y0 + ty, xs = x0 + tx * PX;
+    // flat stage index of this item's group 0 (every item has ngroups stages)
+    const int n0 = it * ngroups;
+    for (int gi = warp; gi < ngroups; gi += NW) {
+      const int n = n0 + gi, s = n % RING;
+      mbar_wait(&full_bar[s], (n / RING) & 1);
+      const float* st = ring + s * T::F2_STAGE;
+      float acc[CC][PX];
+#pragma unroll
+      for (int c = 0; c < CC; ++c)
+#pragma unroll
+        for (int p = 0; p < PX; ++p) acc[c][p] = 0.f;
+#pragma unroll 1
+      for (int dy = 0; dy < ND; ++dy) {
+        float G[ND][PX];
+        const float* gw = gs + dy * BOXG + ty * GW + tx * PX;
+        if (mode == 0) {
+#pragma unroll
+          for (int dx = 0; dx < ND; ++dx)
+#pragma unroll
+            for (int q = 0; q < PX / 4; ++q) {
+              const float4 v = *reinterpret_cast<const float4*>(gw + dx * TH * GW + 4 * q);
+              G[dx][4 * q] = v.x; G[dx][4 * q + 1] = v.y; G[dx][4 * q + 2] = v.z; G[dx][4 * q + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+          for (int dx = 0; dx < ND; ++dx) {
+            float t[PX + 4];
+#pragma unroll
+            for (int q = 0; q < PX / 4 + 1; ++q) {
+              const float4 v = *reinterpret_cast<const float4*>(gw + (2 * D - dx) * TH * GW + (dx & ~3) + 4 * q);
+              t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
+            }
+#pragma unroll
+            for (int p = 0; p < PX; ++p) G[dx][p] = t[p + (dx & 3)];
+          }
+        }
+        const float* pw = st + (ty + dy) * S2 + tx * PX;
+#pragma unroll
+        for (int c = 0; c < CC; ++c) {
+          float w[WIN];
+#pragma unroll
+          for (int q = 0; q < WIN / 4; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(pw + c * F2H * S2 + 4 * q);
+            w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+          }
+#pragma unroll
+          for (int dx = 0; dx < ND; ++dx)
+#pragma unroll
+            for (int p = 0; p < PX; ++p) acc[c][p] = fmaf(G[dx][p], w[p + dx], acc[c][p]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);   // this warp was the only reader of the stage
+      if (y < H && xs < W) {
+#pragma unroll
+        for (int c = 0; c < CC; ++c) {
+          const int ch = gi * CC + c;
+          if (ch < C) {
+            float* o = dout + ((size_t)ch * H + y) * W + xs;
+#pragma unroll
+            for (int q = 0; q < PX / 4; ++q)
+              if (xs + 4 * q < W)
+                *reinterpret_cast<float4*>(o + 4 * q) = make_float4(acc[c][4 * q] * inv_c, acc[c][4 * q + 1] * inv_c, acc[c][4 * q + 2] * inv_c, acc[c][4 * q + 3] * inv_c);
+          }
+        }
+      }
+    }
+    // the coefficient area was modified with generic-proxy stores (mask pass): order them before the TMA (async proxy) refill
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&gfree_bar);   // the coefficient area may be overwritten by the next item
+  }
 }
 
 // generic-displacement backward: one thread per (b, c, y, x) element of d f1 / d f2.
@@ -1293,7 +1491,20 @@ int ocf_corr_bwd_impl(const float* grad_out, const float* out_act, const float* 
     // 61.3 us, L3 43.0 vs 38.8): with 96 registers per thread only ~5 of the 18-24 128-bit loads are in flight, so the lift costs
     // several L2 round trips instead of one TMA round trip.  The staged form stays the default.
     static const int gdirect = []() { const char* e = getenv("OCF_BWD_GDIRECT"); return e ? atoi(e) : 0; }();
-    if (tma && gdirect) {
+    // channel-split persistent form (experiment, OCF_BWD_CS=1): full grids only, sign bitmask or no activation.  Measured SLOWER
+    // than the tiled form (L2 level 79 vs 60 us, C = 64: 132 vs 101, C = 128: 228 vs 181): with the coefficients resident in
+    // shared memory only 4 feature stages fit, i.e. 4 compute warps per SM -- one per scheduler, issue_active 40 %, fma 29 % -- and
+    // every item pays a serial coefficient refill.  No barriers in the main loop, but too little parallelism to profit.
+    static const int use_cs = []() { const char* e = getenv("OCF_BWD_CS"); return e ? atoi(e) : 0; }();
+    const long long nitems = (long long)gx * gy * B * nmodes;
+    if (tma && use_cs && out_act == nullptr && nitems >= OCF_SM_COUNT && nitems < (1LL << 30)) {
+      constexpr int NW = 4, RING = 4;
+      auto kernel = corr_bwd_cs<T, NW, RING>;
+      const size_t csmem = sizeof(float) * ((size_t)T::ND * T::ND * T::TH * T::S2 + (size_t)RING * T::F2_STAGE);
+      if (int e = set_smem(kernel, csmem)) return e;
+      if (int e = launch_kernel(kernel, dim3(OCF_SM_COUNT), (NW + 1) * 32, csmem, s, 1, m1, m2, mg, mask, df1, df2, C, H, W, inv_c, leaky_slope, nmodes,
+                                first, gx, gy, (int)nitems)) return e;
+    } else if (tma && gdirect) {
       auto kernel = corr_bwd_tiled<T, BWD_CR, STG_TMA, true>;
       if (int e = set_smem(kernel, smem)) return e;
       if (int e = launch_kernel(kernel, grid, T::THREADS + 32, smem, s, 1, m1, m2, mg, grad_out, out_act, mask, f1, f2, df1, df2, C, H, W, g_bstride,

@@ -37,7 +37,30 @@ pack_pairs_kernel(const unsigned char* __restrict__ img1, const unsigned char* _
   }
 }
 
+// FlyingChairs2 occlusion mask (models/data/datasets.py:660-669): uint8 [H0,W0] as decoded -> crop -> float -> ToTensor (no
+// scaling for a float array) -> occ[occ > 0.5] = 1 ; occ[occ != 1] = 0, i.e. 1.0 where the decoded value is non-zero
+__global__ void __launch_bounds__(PT)
+pack_occ_kernel(const unsigned char* __restrict__ occ_u8, float* __restrict__ occ, int H0, int W0, int H, int W, int y0, int x0) {
+  const int p = blockIdx.x * PT + threadIdx.x;
+  if (p >= H * W) return;
+  const int b = blockIdx.y;
+  const int y = p / W, x = p - y * W;
+  const float v = (float)occ_u8[((size_t)b * H0 + (y0 + y)) * W0 + (x0 + x)];
+  occ[(size_t)b * H * W + p] = v > 0.5f ? 1.0f : 0.0f;
+}
+
 }  // namespace
+
+extern "C" int ocf_pack_occ(const unsigned char* occ_u8, float* occ, int B, int H0, int W0, int H, int W, int y0, int x0,
+                            ocf_stream_t stream) {
+  OCF_REQUIRE_PTR(occ_u8); OCF_REQUIRE_PTR(occ);
+  OCF_REQUIRE(B > 0 && H0 > 0 && W0 > 0 && H > 0 && W > 0, OCF_ESHAPE);
+  OCF_REQUIRE(y0 >= 0 && x0 >= 0 && y0 + H <= H0 && x0 + W <= W0, OCF_ESHAPE);
+  OCF_REQUIRE(B <= 65535, OCF_EUNSUPPORTED);
+  dim3 grid((H * W + PT - 1) / PT, B);
+  pack_occ_kernel<<<grid, PT, 0, ocf_cast_stream(stream)>>>(occ_u8, occ, H0, W0, H, W, y0, x0);
+  return ocf_launch_status();
+}
 
 extern "C" int ocf_pack_pairs(const unsigned char* img1, const unsigned char* img2, const float* flow_hw2, float* imgs, float* flow,
                               int B, int H0, int W0, int H, int W, int y0, int x0, ocf_stream_t stream) {

@@ -45,3 +45,20 @@ def pack_pairs(img1_u8, img2_u8, flow_hw2=None, crop_size=None, origin=None):
     with torch.cuda.device_of(img1_u8):
         _lib.call("ocf_pack_pairs", _p(img1_u8), _p(img2_u8), _p(flow_hw2), _p(imgs), _p(flow), B, H0, W0, H, W, int(y0), int(x0), _stream())
     return imgs, flow
+
+
+def pack_occ(occ_u8, crop_size=None, origin=None):
+    """occ_u8: CUDA uint8 [B,H0,W0] (the decoded FlyingChairs2 `*-occ_01.png`).  Returns the [B,1,H,W] fp32 {0,1} mask of
+    models/data/datasets.py:660-669 for the crop (default: the reference's centre crop to a multiple of 64)."""
+    if not isinstance(occ_u8, torch.Tensor) or not occ_u8.is_cuda:
+        raise TypeError("occ_u8 must be a CUDA tensor: ocflow_b200 has no CPU path")
+    if occ_u8.dtype != torch.uint8 or occ_u8.dim() != 3:
+        raise TypeError("occ_u8 must be uint8 [B,H,W] (got %s %s)" % (occ_u8.dtype, tuple(occ_u8.shape)))
+    occ_u8 = occ_u8.contiguous()
+    B, H0, W0 = occ_u8.shape
+    H, W = crop_size if crop_size is not None else render_size((H0, W0))
+    y0, x0 = origin if origin is not None else center_crop_origin((H0, W0), (H, W))
+    occ = torch.empty((B, 1, H, W), device=occ_u8.device, dtype=torch.float32)
+    with torch.cuda.device_of(occ_u8):
+        _lib.call("ocf_pack_occ", _p(occ_u8), _p(occ), B, H0, W0, H, W, int(y0), int(x0), _stream())
+    return occ

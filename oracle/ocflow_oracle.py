@@ -339,6 +339,19 @@ def pack_pairs(img1_u8, img2_u8, flow_hw2=None):
 # --------------------------------------------------------------------------------------------
 
 
+def pack_occ(occ_u8):
+    """FlyingChairs2 ground-truth occlusion mask, models/data/datasets.py:660-669: decoded uint8 [H0,W0] -> float32 ->
+    StaticCenterCrop to a multiple of 64 -> ToTensor (a float array is not rescaled) -> occ[occ > 0.5] = 1 ; occ[occ != 1] = 0.
+    occ_u8: uint8 [B,H0,W0] -> float32 [B,1,H,W]."""
+    B, H0, W0 = occ_u8.shape
+    th, tw = (H0 // 64) * 64, (W0 // 64) * 64
+    y0, x0 = (H0 - th) // 2, (W0 - tw) // 2
+    occ = occ_u8[:, y0:y0 + th, x0:x0 + tw].to(torch.float32).unsqueeze(1).clone()
+    occ[occ > 0.5] = 1.0
+    occ[occ != 1.0] = 0.0
+    return occ
+
+
 def flow_error(tu, tv, u, v):
     """Average end-point error (flow_utils.py:179-232, occ=None): ground truth above 1e7 in magnitude marks unknown
     pixels, which are zeroed in all four maps (so they contribute 0 and still count in the mean)."""

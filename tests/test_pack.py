@@ -61,3 +61,52 @@ def test_cuda_pack_matches_reference_fixture_bit_exact():
         data.pack_pairs(i1, i1)
     with pytest.raises(RuntimeError):
         data.pack_pairs(i1.cuda(), i1.cuda(), None, crop_size=(64, 64), origin=(10, 40))   # window leaves the frame
+
+
+def _reference_occ(occ_np):
+    """The reference's own statements for one sample (models/data/datasets.py:660-669) with its StaticCenterCrop and
+    torchvision's ToTensor, imported from the installed reference when it is present."""
+    import importlib
+    import sys
+
+    from oracle import ref_loader
+    from torchvision import transforms
+
+    ref_loader.load()
+    if not hasattr(sys.modules.get("imageio"), "imread"):      # empty stub installed by ref_loader; never called on this path
+        sys.modules["imageio"].imread = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("imageio is not installed"))
+    ds = importlib.import_module("models.data.datasets")
+
+    h, w = occ_np.shape
+    cropper = ds.StaticCenterCrop((h, w), [(h // 64) * 64, (w // 64) * 64])
+    occ = cropper(occ_np.astype(np.float32)[:, :, None])     # StaticCenterCrop indexes three axes: a decoded mask is [H,W,1]
+    occ = transforms.ToTensor()(occ)
+    occ[occ > 0.5] = 1.0
+    occ[occ != 1.0] = 0.0
+    return occ
+
+
+def test_oracle_pack_occ_matches_the_reference_statements():
+    from oracle import ref_loader
+
+    rng = np.random.default_rng(11)
+    occ = (rng.random((2, 100, 140)) < 0.3).astype(np.uint8) * 255
+    occ[0, 20:30, 40:50] = 1          # any non-zero decoded value is "occluded"
+    mine = O.pack_occ(torch.from_numpy(occ))
+    assert mine.shape == (2, 1, 64, 128) and set(mine.unique().tolist()) <= {0.0, 1.0}
+    if ref_loader.available():
+        for b in range(2):
+            assert torch.equal(mine[b], _reference_occ(occ[b]))
+
+
+@pytest.mark.gpu
+def test_cuda_pack_occ_bit_exact():
+    from ocflow_b200 import data
+
+    rng = np.random.default_rng(12)
+    occ = torch.from_numpy((rng.integers(0, 4, (3, 436, 1024)) == 0).astype(np.uint8) * rng.integers(1, 256, (3, 436, 1024), dtype=np.uint8))
+    assert torch.equal(data.pack_occ(occ.cuda()).cpu(), O.pack_occ(occ))
+    win = data.pack_occ(occ.cuda(), crop_size=(64, 128), origin=(5, 7)).cpu()
+    assert torch.equal(win, (occ[:, 5:69, 7:135] > 0).float().unsqueeze(1))
+    with pytest.raises(TypeError):
+        data.pack_occ(occ)
