@@ -96,12 +96,24 @@ class FlowNetCV(nn.Module):
         flow = getattr(self, "predict_flow%d" % lvl)(x)
         return x, flow
 
+    # set by train.TrainStep: called from the backward pass when the gradient of the encoder's output arrives, i.e. when every
+    # decoder / context-network gradient is final and only the encoder's backward is left (autograd runs the nodes created first
+    # -- the encoder -- last)
+    decoder_grads_done_hook = None
+
+    def encoder_parameters(self):
+        for name, _, _, _ in _ENCODER:
+            yield from getattr(self, name).parameters()
+
     def pyramids(self, x):
         """Feature pyramids of both images with ONE pass of the (weight-shared) encoder over a 2B batch: the reference runs
         the same 18 convolutions twice (cost_volume_flow_net.py:158-169); per-sample results are identical."""
         B, _, H, W = x.shape
         both = x.reshape(B, 2, 3, H, W).transpose(0, 1).reshape(2 * B, 3, H, W)
         feats = self.pyramid(both)
+        if self.decoder_grads_done_hook is not None and feats[6].requires_grad:
+            hook = self.decoder_grads_done_hook
+            feats[6].register_hook(lambda g: hook())     # returns None: the gradient is not modified
         return {l: f[:B] for l, f in feats.items()}, {l: f[B:] for l, f in feats.items()}
 
     def decode(self, p1, p2):

@@ -3,8 +3,9 @@ backward / Adam.step, models/model.py:508-509), data-parallel over the GPUs of o
 
 One process per GPU.  Work is sharded by batch of image pairs; every hot-path op is per-sample, so the only
 exchange is the gradient all-reduce (mean) of the 9.37 M fp32 parameters: all parameter gradients live in ONE flat
-buffer (each `p.grad` is a view), so the exchange is a single in-place NCCL all-reduce of 37.5 MB over
-NVLink/NVSwitch per step -- no bucketing, no copies.  (no collective follows a hot-path
+buffer (each `p.grad` is a view), reduced in place by NCCL over NVLink/NVSwitch in two slices -- everything but the shared
+encoder (36 of the 37.5 MB) on a side stream as soon as the decoders' backward is complete, overlapped with the encoder's
+backward, then the encoder slice -- with the 1 / world factor folded into the loss; no copies.  (no collective follows a hot-path
 kernel directly, so there is nothing to fuse a collective into.)
 
 The whole step (2 network forwards, loss kernels, backward, all-reduce, Adam) can be captured in one CUDA graph
@@ -25,10 +26,15 @@ DEFAULT_HPARAMS = {
 
 
 class FlatGrads:
-    """All gradients of `params` as views of one contiguous buffer (zero-copy single-collective all-reduce)."""
+    """All gradients of `params` as views of one contiguous buffer (zero-copy collectives).  `late` (optional): parameters whose
+    gradients complete LAST in the backward pass (the shared encoder); they are placed first, so that flat[n_late:] -- everything
+    else -- is one contiguous slice that can be reduced while the backward pass is still running."""
 
-    def __init__(self, params):
-        self.params = [p for p in params if p.requires_grad]
+    def __init__(self, params, late=()):
+        late_ids = {id(p) for p in late}
+        params = [p for p in params if p.requires_grad]
+        self.params = [p for p in params if id(p) in late_ids] + [p for p in params if id(p) not in late_ids]
+        self.n_late = sum(p.numel() for p in self.params if id(p) in late_ids)
         total = sum(p.numel() for p in self.params)
         ref = self.params[0]
         self.flat = torch.zeros(total, device=ref.device, dtype=ref.dtype)
@@ -40,6 +46,14 @@ class FlatGrads:
 
     def zero_(self):
         self.flat.zero_()
+
+    def all_reduce_sum(self, lo=0, hi=None, group=None):
+        """flat[lo:hi] <- sum over ranks, in place.  No-op without an initialised process group / with world size 1."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        part = self.flat if (lo == 0 and hi is None) else self.flat[lo:hi]
+        if part.numel():
+            dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
 
     def all_reduce_mean(self, group=None):
         """grad <- mean over ranks.  No-op without an initialised process group / with world size 1."""
@@ -60,19 +74,55 @@ class TrainStep:
         self.group = group
         self.use_graph = bool(use_graph)
         lr = model.lr if lr is None else lr
-        self.grads = FlatGrads(model.parameters())
+        # Gradient exchange: the loss is scaled by 1 / world, so a SUM all-reduce yields the mean gradient (no extra pass over the
+        # buffer).  With a FlowNetCV inside, everything but the shared encoder is reduced on a side stream as soon as the decoders'
+        # backward is complete -- overlapped with the encoder's backward -- and the encoder slice follows at the end.
+        net = getattr(model, "flow_pred", None)
+        late = list(net.encoder_parameters()) if hasattr(net, "encoder_parameters") else []
+        self.grads = FlatGrads(model.parameters(), late=late)
+        self._overlap = bool(late) and hasattr(net, "decoder_grads_done_hook")
+        self._early_done = False
+        self._side = None
+        if self._overlap:
+            net.decoder_grads_done_hook = self._reduce_early
         self.opt = torch.optim.Adam(model.parameters(), lr, capturable=self.use_graph, foreach=True)
         self.graph = None
         self.static_batch = None
         self.static_loss = None
 
+    def _world(self):
+        return dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+
+    def _reduce_early(self):
+        """Called from the backward pass (autograd hook on the encoder's output) once every non-encoder gradient is final."""
+        if self._world() == 1 or self._early_done:
+            return
+        cur = torch.cuda.current_stream() if self.grads.flat.is_cuda else None
+        if cur is not None:
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                self.grads.all_reduce_sum(self.grads.n_late, None, self.group)
+        else:
+            self.grads.all_reduce_sum(self.grads.n_late, None, self.group)
+        self._early_done = True
+
     def _eager(self, batch):
         self.grads.zero_()
+        world = self._world()
+        self._early_done = False
         scope = self.model.conv_math_scope() if hasattr(self.model, "conv_math_scope") else contextlib.nullcontext()
         with scope:   # forward AND backward convolutions under hparams['conv_math']
             loss = self.model.training_step(batch, 0)
-            loss.backward()
-        self.grads.all_reduce_mean(self.group)
+            (loss if world == 1 else loss * (1.0 / world)).backward()
+        if world > 1:
+            if self._early_done:
+                self.grads.all_reduce_sum(0, self.grads.n_late, self.group)          # the encoder slice
+                if self._side is not None:
+                    torch.cuda.current_stream().wait_stream(self._side)
+            else:
+                self.grads.all_reduce_sum(0, None, self.group)
         self.opt.step()
         return loss.detach()
 

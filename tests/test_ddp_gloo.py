@@ -23,6 +23,38 @@ class ToyStage(nn.Module):
         return ((self.net(imgs) - flow) ** 2 * (1 - occ)).mean()
 
 
+class ToyNet(nn.Module):
+    """Stand-in for FlowNetCV's contract with the step driver: an encoder whose gradients complete last, a hook that fires
+    from the backward pass once everything else is final (flow_net_cv.FlowNetCV.pyramids registers it the same way)."""
+    decoder_grads_done_hook = None
+
+    def __init__(self):
+        super().__init__()
+        self.enc = nn.Sequential(nn.Conv2d(6, 8, 3, padding=1), nn.LeakyReLU(0.1))
+        self.dec = nn.Conv2d(8, 2, 3, padding=1)
+
+    def encoder_parameters(self):
+        return self.enc.parameters()
+
+    def forward(self, x):
+        f = self.enc(x)
+        if self.decoder_grads_done_hook is not None and f.requires_grad:
+            hook = self.decoder_grads_done_hook
+            f.register_hook(lambda g: hook())
+        return self.dec(f)
+
+
+class ToyStageOverlap(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.lr = 1e-2
+        self.flow_pred = ToyNet()
+
+    def training_step(self, batch, batch_idx):
+        imgs, flow, occ = batch
+        return ((self.flow_pred(imgs) - flow) ** 2 * (1 - occ)).mean()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -66,6 +98,20 @@ def _worker(rank, world, port, out):
         assert torch.equal(allp[0], allp[1])
         for _ in range(2):
             step.step(batch)
+        # the two-slice exchange (everything but the encoder reduced from inside the backward pass, the encoder slice at the end)
+        torch.manual_seed(1)
+        m2 = ToyStageOverlap()
+        s2 = TrainStep(m2, use_graph=False)
+        assert s2._overlap and 0 < s2.grads.n_late < s2.grads.flat.numel()
+        r2 = ToyStageOverlap()
+        r2.load_state_dict(m2.state_dict())
+        r2.training_step(batch, 0).backward()
+        local2 = torch.cat([p.grad.reshape(-1) for p in list(r2.flow_pred.enc.parameters()) + list(r2.flow_pred.dec.parameters())])
+        g2 = [torch.zeros_like(local2) for _ in range(world)]
+        dist.all_gather(g2, local2)
+        l2 = s2.step(batch)
+        assert s2._early_done and torch.isfinite(l2)
+        assert torch.allclose(s2.grads.flat, torch.stack(g2).mean(0), rtol=1e-6, atol=1e-8)
         out.put((rank, float(loss)))
     finally:
         dist.destroy_process_group()
