@@ -122,6 +122,12 @@ warp_fwd_kernel(const float* __restrict__ img, const float* __restrict__ flow, c
   }
 }
 
+// (Measured dead end, twice: a "quad" forward -- a thread owns 4 adjacent samples, the 5 + 5 source pixels of a coherent quad fetched
+// as 4 x LDG.128 and aligned with a register funnel, channels in batches of 4 -- issues 3.7x fewer instructions and half the L1
+// wavefronts per sample, and is 1.4-2.5x SLOWER at every size (8x32x188x620: 104-156 us against 73-78 us for the kernel above;
+// 8x128x188x620: 674 vs 265 us): with 4x fewer threads the gather has less memory-level parallelism than the one-sample-per-
+// thread form, whose neighbouring lanes share L1 lines anyway.)
+
 // Backward.  d_img is a scatter (red.global.add.f32, zeroed by the entry point); d_flow / d_occ are per-pixel and
 // accumulated across channel slabs with one atomic per slab (plain store when there is 1 slab).
 // Lanes are 32 horizontally adjacent samples, so for a spatially coherent flow (what the decoders produce: an up-sampled
@@ -129,6 +135,10 @@ warp_fwd_kernel(const float* __restrict__ img, const float* __restrict__ flow, c
 // path then retires ~1.1 T elements/s, against 0.18 T/s for incoherent addresses -- and the east taps of lane l coincide
 // with the west taps of lane l+1: that coincidence is detected once per sample (it does not depend on the channel) and the
 // two contributions are summed with one shuffle, halving the red operations.
+// (Measured: collecting the left-over east taps of lane 31 of a whole channel batch into ONE red -- 17 instead of 32 red
+// instructions per 8 channels -- changes nothing (210 vs 209 us at 8x32x188x620, range map likewise): at that size the scatter is
+// bound by the DRAM traffic of the zero-fill + read-modify-write of d_img (dram_rd 365 MB for 238 MB of inputs), not by the
+// number of red instructions.)
 template <int CB>
 __global__ void __launch_bounds__(WARP_THREADS, 2)
 warp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ img, const float* __restrict__ flow,
