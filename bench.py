@@ -722,7 +722,9 @@ def main():
     # ---- roofline of the dominant hot-path kernel ----
     if not args.skip_roofline:
         peak, peak_src = measured_peaks()
-        kt = time_kernels(args, torch)                           # alone, L2 flushed before every launch
+        kt = time_kernels(args, torch, with_copy_ref=(world == 1))   # alone, L2 flushed before every launch (+ a plain copy of the same bytes)
+        copy_us = {k[len("copy_same_bytes:"):]: v["us"] for k, v in kt.items() if k.startswith("copy_same_bytes:")}
+        kt = {k: v for k, v in kt.items() if not k.startswith("copy_same_bytes:")}
         # live pass: inside real steps, CUDA events on the launching stream (N=1 only: the eager step of a multi-rank job
         # contains the all-reduce, which rank 0 cannot run alone)
         live = live_kernel_times(step, batch, torch, H) if world == 1 else {k: (v["us"], v["per_step"]) for k, v in kt.items()}
@@ -745,7 +747,9 @@ def main():
         line["kernels"] = {k: {"us": round(v["us"], 2), "gbs": round(v["gbs"], 1), "frac": round(v["gbs"] / peak, 3),
                                "per_step": v["per_step"],
                                "live_us": round(live[k][0], 2) if k in live else None,
-                               "live_frac": round(v["bytes"] / (live[k][0] * 1e-6) / 1e9 / peak, 3) if k in live else None}
+                               "live_frac": round(v["bytes"] / (live[k][0] * 1e-6) / 1e9 / peak, 3) if k in live else None,
+                               # the harness ceiling at this size: a plain torch copy moving the same number of bytes, same flush
+                               "copy_same_bytes_us": round(copy_us[k], 2) if k in copy_us else None}
                            for k, v in kt.items()}
         line["hot_path_us_per_step"] = round(sum(v["us"] * v["per_step"] for v in kt.values()), 1)
         if world == 1:

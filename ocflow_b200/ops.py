@@ -93,6 +93,10 @@ def cost_volume(f1, f2, max_displacement=4, leaky_slope=1.0):
     f2 = _req(f2, "features2", 4)
     if f1.shape != f2.shape:
         raise ValueError("features1 and features2 must have the same shape (got %s vs %s)" % (tuple(f1.shape), tuple(f2.shape)))
+    if f1.numel() == 0:
+        # empty batch / empty image: the reference's slice-multiply-mean chain returns an empty cost volume
+        nd = 2 * int(max_displacement) + 1
+        return (f1.sum() + f2.sum()) * 0 + f1.new_zeros((f1.shape[0], nd * nd, f1.shape[2], f1.shape[3]))
     W = f1.shape[3]
     if W % 4 != 0 and int(max_displacement) == 4 and W >= 16:
         # Ragged rows (KITTI / Sintel pyramids: 621, 311, 39 ...) cannot be described to the TMA unit (global strides must be
@@ -309,6 +313,8 @@ def warp(img, flow, align_corners=True, is_mask=False, occ=None, flow_scale=1.0)
         occ = _req(occ, "occ", 4)
         if occ.shape != (B, 1, H, W):
             raise ValueError("occ must be [B,1,H,W]")
+    if img.numel() == 0:
+        return (img.sum() + flow.sum()) * 0 + torch.zeros_like(img)      # empty batch: nothing to sample (grad-connected like the op)
     flags = (WARP_ALIGN_CORNERS if align_corners else 0) | (WARP_IS_MASK if is_mask else 0)
     return _Warp.apply(img, flow, occ, flags, float(flow_scale))
 
@@ -360,6 +366,8 @@ def range_map(flow, with_occlusion=False):
         raise ValueError("flow must be [B,2,H,W]")
     rmap = torch.empty((B, 1, H, W), device=flow.device, dtype=torch.float32)
     occ = torch.empty_like(rmap) if with_occlusion else None
+    if rmap.numel() == 0:
+        return (rmap, occ) if with_occlusion else rmap
     with torch.cuda.device_of(flow):
         _lib.call("ocf_range_map", _p(flow), _p(rmap), _p(occ), B, H, W, _stream())
     if with_occlusion:

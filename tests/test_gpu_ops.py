@@ -328,3 +328,19 @@ def test_corr_d10_tiled_forward_matches_oracle(B, C, H, W, slope):
     g1, g2 = torch.autograd.grad((out * cot.cuda()).sum(), (x1, x2))
     assert_close(g1, ga, TOL, "corr d=10 grad f1")
     assert_close(g2, gb, TOL, "corr d=10 grad f2")
+
+
+def test_empty_batches_return_empty_results_like_the_reference():
+    """B = 0 (and zero-sized images): the reference's tensor ops return empty tensors of the right shape; so do the wrappers
+    (no kernel is launched)."""
+    from ocflow_b200 import ops
+
+    f = torch.zeros(0, 8, 6, 7, device="cuda", requires_grad=True)
+    fl = torch.zeros(0, 2, 6, 7, device="cuda")
+    cv = ops.cost_volume(f, f, 4)
+    assert cv.shape == (0, 81, 6, 7) and cv.requires_grad
+    assert ops.cost_volume(f, f, 10).shape == (0, 441, 6, 7)
+    assert ops.warp(f, fl, align_corners=False).shape == (0, 8, 6, 7)
+    assert ops.range_map(fl).shape == (0, 1, 6, 7)
+    ref = O.cost_volume(torch.zeros(0, 8, 6, 7), torch.zeros(0, 8, 6, 7), 4)
+    assert ref.shape == cv.shape
