@@ -143,6 +143,16 @@ __device__ __forceinline__ void tma_load_4d(float* smem_dst, const CUtensorMap* 
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(c), "r"(b)
       : "memory");
 }
+// dense [c][y][x] box in shared memory -> one 4-D box {x, y, c, b} of an NCHW fp32 tensor (elements outside the tensor are dropped)
+__device__ __forceinline__ void tma_store_4d(const float* smem_src, const CUtensorMap* map, int x, int y, int c, int b) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(smem_src)), "r"(x), "r"(y), "r"(c), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- packed fp32 FMA (Blackwell FFMA2): two IEEE fp32 fused multiply-adds per issue slot ------------
 typedef unsigned long long u64;
 template <int V>
@@ -466,9 +476,13 @@ corr_fwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
 // running ACROSS tile boundaries: while the warps finish tile t and store its 81 planes, the boxes of tile t+1 are
 // already in flight, so only the first tile of a CTA pays the cold-start latency (at C = 32 a tile is just 4 chunks --
 // without this every tile would wait ~1.5 us for its first box with nothing else to do).
-template <class T, int UNROLL>
+// TMAST: the epilogue goes through shared memory and TMA stores.  Every dy-warp owns a [9 planes][TH][TW] staging box; after a
+// tile's main loop it waits until the TMA unit has read its previous box, writes the activated values (128-bit shared stores),
+// and lane 0 issues ONE cp.async.bulk.tensor store for the 9 planes -- no per-thread global stores, no bounds predicates (the TMA
+// unit clips at the image border), and the copy-out runs while the warp is already in the next tile's main loop.
+template <class T, int UNROLL, bool TMAST = false>
 __global__ void __maxnreg__(OCF_FWD_REGS)
-corr_fwd_persist(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2, float* __restrict__ out,
+corr_fwd_persist(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap mapo, float* __restrict__ out,
                  unsigned char* __restrict__ mask, int C, int H, int W, long long out_bstride, float inv_c, float slope, int tiles_x,
                  int tiles_y, int ntiles) {
   constexpr int D = T::D, PX = T::PX, ND = T::ND, TH = T::TH, TW = T::TW, CC = T::CC, STAGES = T::STAGES;
@@ -581,6 +595,11 @@ corr_fwd_persist(const __grid_constant__ CUtensorMap map1, const __grid_constant
     const bool inside = y < H && xs < W;
     float* ob = out + (size_t)b * bstride + ((size_t)(dyi * ND) * H + y) * W + xs;
     const int Wb = (W + 7) >> 3;
+    float* stg = smem + STAGES * STAGE + dyi * (ND * TH * TW);   // TMAST: this warp's [ND][TH][TW] staging box
+    if constexpr (TMAST) {
+      if (lane == 0) tma_store_wait_read();   // the previous tile's box of this warp has been read by the TMA unit
+      __syncwarp();
+    }
 #pragma unroll
     for (int dx = 0; dx < ND; ++dx) {
       float rr[PX];
@@ -600,12 +619,24 @@ corr_fwd_persist(const __grid_constant__ CUtensorMap map1, const __grid_constant
         mbyte |= (v > 0.f ? 1u : 0u) << p;
         rr[p] = v > 0.f ? v : v * slope;
       }
-      if (inside) {
-        if (mask != nullptr) mask[(((size_t)b * ND * ND + dyi * ND + dx) * H + y) * Wb + (xs >> 3)] = (unsigned char)mbyte;
+      if (inside && mask != nullptr) mask[(((size_t)b * ND * ND + dyi * ND + dx) * H + y) * Wb + (xs >> 3)] = (unsigned char)mbyte;
+      if constexpr (TMAST) {
+        float* sp = stg + (dx * TH + ty) * TW + tx * PX;
+#pragma unroll
+        for (int q = 0; q < PX / 4; ++q) *reinterpret_cast<float4*>(sp + 4 * q) = make_float4(rr[4 * q], rr[4 * q + 1], rr[4 * q + 2], rr[4 * q + 3]);
+      } else if (inside) {
         float* o = ob + (size_t)dx * H * W;
 #pragma unroll
         for (int q = 0; q < PX / 4; ++q)
           if (xs + 4 * q < W) *reinterpret_cast<float4*>(o + 4 * q) = make_float4(rr[4 * q], rr[4 * q + 1], rr[4 * q + 2], rr[4 * q + 3]);
+      }
+    }
+    if constexpr (TMAST) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the TMA unit
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_4d(stg, &mapo, txi * TW, tyi * TH, dyi * ND, b);
+        tma_store_commit();
       }
     }
 #pragma unroll
@@ -615,6 +646,9 @@ corr_fwd_persist(const __grid_constant__ CUtensorMap map1, const __grid_constant
       for (int j = 0; j < D; ++j) accp[p][j] = 0ull;
     }
     if (k < 3) OCF_TL(3 + 2 * k);
+  }
+  if constexpr (TMAST) {
+    if (lane == 0) tma_store_wait_all();   // the stores must have completed before the CTA (and its shared memory) goes away
   }
   OCF_TL(14);
 }
@@ -1225,6 +1259,7 @@ using Tile10 = CorrTile<10, 4, 8, 4, 8, 3, 7, 128>;
 #define OCF_FWD_STAGES 6
 #endif
 using Tile4P = CorrTile<4, 8, 4, 8, 8, OCF_FWD_STAGES>;  // persistent forward: one CTA per SM, deep ring
+using Tile4PS = CorrTile<4, 8, 4, 8, 8, 4>;              // ... with the TMA-store epilogue: 4 stages + 81 staged output planes
 constexpr int BWD_CR = 4;
 constexpr int FWD_UNROLL = OCF_FWD_UNROLL;
 
@@ -1394,14 +1429,25 @@ static int corr_fwd_impl(const float* f1, long long f1_bstride, const float* f2,
     const bool tma = vec && (f1_bstride % 4 == 0) && make_map(&m1, f1, B, C, H, W, T::S1, T::TH, T::CC, f1_bstride) &&
                      make_map(&m2, f2, B, C, H, W, T::S2, T::F2H, T::CC);
     OCF_REQUIRE(tma || f1_bstride == 0, OCF_EUNSUPPORTED);
-    if (tma && ks == 1) {
+    static const int tma_store = []() { const char* e = getenv("OCF_FWD_TMA_STORE"); return e ? atoi(e) : 1; }();   // developer knob (A/B runs)
+    CUtensorMap mo;
+    memset(&mo, 0, sizeof(mo));
+    if (tma && ks == 1 && tma_store && make_map(&mo, out, B, 81, H, W, T::TW, T::TH, T::ND, out_bstride)) {
+      using TP = Tile4PS;
+      auto kernel = corr_fwd_persist<TP, FWD_UNROLL, true>;
+      const size_t psmem = sizeof(float) * (TP::STAGES * (TP::F1_STAGE + TP::F2_STAGE) + TP::ND * TP::ND * TP::TH * TP::TW);
+      if (int e = set_smem(kernel, psmem)) return e;
+      const int ntiles = gx * gy * B;
+      const int nblk = ntiles < OCF_FWD_CTAS_PER_SM * OCF_SM_COUNT ? ntiles : OCF_FWD_CTAS_PER_SM * OCF_SM_COUNT;
+      if (int e = launch_kernel(kernel, dim3(nblk), TP::THREADS, psmem, s, 1, m1, m2, mo, out, mask_out, C, H, W, out_bstride, inv_c, leaky_slope, gx, gy, ntiles)) return e;
+    } else if (tma && ks == 1) {
       using TP = Tile4P;
       auto kernel = corr_fwd_persist<TP, FWD_UNROLL>;
       const size_t psmem = sizeof(float) * TP::STAGES * (TP::F1_STAGE + TP::F2_STAGE);
       if (int e = set_smem(kernel, psmem)) return e;
       const int ntiles = gx * gy * B;
       const int nblk = ntiles < OCF_FWD_CTAS_PER_SM * OCF_SM_COUNT ? ntiles : OCF_FWD_CTAS_PER_SM * OCF_SM_COUNT;
-      if (int e = launch_kernel(kernel, dim3(nblk), TP::THREADS, psmem, s, 1, m1, m2, out, mask_out, C, H, W, out_bstride, inv_c, leaky_slope, gx, gy, ntiles)) return e;
+      if (int e = launch_kernel(kernel, dim3(nblk), TP::THREADS, psmem, s, 1, m1, m2, mo, out, mask_out, C, H, W, out_bstride, inv_c, leaky_slope, gx, gy, ntiles)) return e;
     } else if (tma) {
       auto kernel = corr_fwd_tiled<T, STG_TMA>;
       if (int e = set_smem(kernel, smem)) return e;
