@@ -522,11 +522,19 @@ corr_fwd_persist(const __grid_constant__ CUtensorMap map1, const __grid_constant
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ND); }
     mbar_fence_init();
-#pragma unroll
-    for (int s = 0; s < STAGES; ++s)
-      if (pn < total) issue_next();
   }
   __syncthreads();
+  if (dyi == ND) {
+    // dedicated producer warp (the CTA is alone on its SM, so the extra warp is free): the compute warps never wait for a stage
+    // to drain -- when thread 0 doubled as the producer, warp 0 stalled on the slowest warp once per chunk
+    if (lane == 0) {
+      for (int n = 0; n < total; ++n) {
+        if (n >= STAGES) mbar_wait(&empty_bar[n % STAGES], ((n / STAGES) - 1) & 1);
+        issue_next();
+      }
+    }
+    return;
+  }
 
   u64 accp[PX][D];
   float accs[PX];
@@ -543,11 +551,6 @@ corr_fwd_persist(const __grid_constant__ CUtensorMap map1, const __grid_constant
   for (int k = 0; k < ntl; ++k) {
     for (int i = 0; i < nchunks; ++i, ++n) {
       const int s = n % STAGES;
-      // refill the stage released one step ago (deferred so that thread 0 does not wait for the slowest warp)
-      if (tid == 0 && n >= 1 && pn < total) {
-        mbar_wait(&empty_bar[(n - 1) % STAGES], ((n - 1) / STAGES) & 1);
-        issue_next();
-      }
       mbar_wait(&full_bar[s], (n / STAGES) & 1);
       if (n == 0) OCF_TL(1);
       const float* st = smem + s * STAGE;
@@ -1439,7 +1442,7 @@ static int corr_fwd_impl(const float* f1, long long f1_bstride, const float* f2,
       if (int e = set_smem(kernel, psmem)) return e;
       const int ntiles = gx * gy * B;
       const int nblk = ntiles < OCF_FWD_CTAS_PER_SM * OCF_SM_COUNT ? ntiles : OCF_FWD_CTAS_PER_SM * OCF_SM_COUNT;
-      if (int e = launch_kernel(kernel, dim3(nblk), TP::THREADS, psmem, s, 1, m1, m2, mo, out, mask_out, C, H, W, out_bstride, inv_c, leaky_slope, gx, gy, ntiles)) return e;
+      if (int e = launch_kernel(kernel, dim3(nblk), TP::THREADS + 32, psmem, s, 1, m1, m2, mo, out, mask_out, C, H, W, out_bstride, inv_c, leaky_slope, gx, gy, ntiles)) return e;
     } else if (tma && ks == 1) {
       using TP = Tile4P;
       auto kernel = corr_fwd_persist<TP, FWD_UNROLL>;
@@ -1447,7 +1450,7 @@ static int corr_fwd_impl(const float* f1, long long f1_bstride, const float* f2,
       if (int e = set_smem(kernel, psmem)) return e;
       const int ntiles = gx * gy * B;
       const int nblk = ntiles < OCF_FWD_CTAS_PER_SM * OCF_SM_COUNT ? ntiles : OCF_FWD_CTAS_PER_SM * OCF_SM_COUNT;
-      if (int e = launch_kernel(kernel, dim3(nblk), TP::THREADS, psmem, s, 1, m1, m2, mo, out, mask_out, C, H, W, out_bstride, inv_c, leaky_slope, gx, gy, ntiles)) return e;
+      if (int e = launch_kernel(kernel, dim3(nblk), TP::THREADS + 32, psmem, s, 1, m1, m2, mo, out, mask_out, C, H, W, out_bstride, inv_c, leaky_slope, gx, gy, ntiles)) return e;
     } else if (tma) {
       auto kernel = corr_fwd_tiled<T, STG_TMA>;
       if (int e = set_smem(kernel, smem)) return e;
