@@ -710,6 +710,7 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload(H, W, B),
                    "global_batch": world * B, "parallelism": "dp%d" % world, "cuda_graph": bool(args.graph),
+                   "streams": "the swapped pair's no-grad decode runs on a side stream next to the main decode (two branches of the step's graph)",
                    "conv_math": "tf32 (torch default)" if args.tf32 else "strict fp32 (cudnn.allow_tf32=False)",
                    "l2_policy": "working set per step (>1 GB of activations) exceeds the 126 MB L2; kernel-alone timings flush L2 "
                                 "with a 1 GiB memset between launches"},

@@ -10,6 +10,8 @@ statistics pass, an apply pass that leaves the normalised c1 where the decoder's
 which reads it in place and writes the cost volume into the same buffer).  The convolution stacks stay on cuDNN (out of
 scope); the x4 flow up-sampling at the end (:245) is `ops.resize_bilinear`.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -79,6 +81,9 @@ class FlowNetCV(nn.Module):
 
     # hparams-free switch (not a reference hyper-parameter): False runs the level as 5 separate ops + torch.cat
     fused_level = True
+    # forward_bidirectional: run the swapped pair's no-grad decode on a side stream (False: one after the other)
+    overlap_decodes = os.environ.get("OCF_OVERLAP_DECODES", "1") == "1"
+    _side = None
 
     def _level(self, lvl, c1, c2, up_flow, up_feat):
         if self.fused_level and self.displacement == 4:
@@ -145,7 +150,22 @@ class FlowNetCV(nn.Module):
         if x.dim() != 4 or x.shape[1] != 6:
             raise ValueError("FlowNetCV expects [B,6,H,W] (two RGB images), got %s" % (tuple(x.shape),))
         p1, p2 = self.pyramids(x)
-        flow1, flow_l2 = self.decode(p1, p2)
-        with torch.no_grad():
+        if not (self.overlap_decodes and x.is_cuda):
+            flow1, flow_l2 = self.decode(p1, p2)
+            with torch.no_grad():
+                back_flow1, _ = self.decode({l: f.detach() for l, f in p2.items()}, {l: f.detach() for l, f in p1.items()})
+            return flow1, flow_l2, back_flow1
+        # The two decodes are independent once the pyramids exist, and the coarse levels (6x8 ... 24x32 pixels per item) leave most
+        # of the 148 SMs idle: the no-grad decode of the swapped pair runs on a side stream next to the main one (fork / join by
+        # events, so it is captured as a parallel branch of the step's CUDA graph).
+        cur = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        side = self._side
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), torch.no_grad():
             back_flow1, _ = self.decode({l: f.detach() for l, f in p2.items()}, {l: f.detach() for l, f in p1.items()})
+        flow1, flow_l2 = self.decode(p1, p2)
+        cur.wait_stream(side)
+        back_flow1.record_stream(cur)     # allocated on the side stream, consumed on the current one
         return flow1, flow_l2, back_flow1
