@@ -12,6 +12,7 @@ The whole step (2 network forwards, loss kernels, backward, all-reduce, Adam) ca
 (`use_graph=True`): shapes are static, every C-ABI call enqueues on torch's current stream and never synchronises.
 """
 import contextlib
+import os
 
 import torch
 import torch.distributed as dist
@@ -85,7 +86,10 @@ class TrainStep:
         self._side = None
         if self._overlap:
             net.decoder_grads_done_hook = self._reduce_early
-        self.opt = torch.optim.Adam(model.parameters(), lr, capturable=self.use_graph, foreach=True)
+        # one fused multi-tensor Adam kernel on CUDA (same update formula as the reference's torch.optim.Adam, models/model.py:508-509)
+        on_cuda = next(model.parameters()).is_cuda
+        fused = on_cuda and os.environ.get("OCF_FUSED_ADAM", "1") == "1"
+        self.opt = torch.optim.Adam(model.parameters(), lr, capturable=self.use_graph, foreach=None if fused else True, fused=fused or None)
         self.graph = None
         self.static_batch = None
         self.static_loss = None
