@@ -127,6 +127,16 @@ int ocf_normalize_bwd(const float* const* grad_ys, const float* const* xs, float
                       ocf_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Bias + LeakyReLU epilogue of the FlowNetCV convolution blocks (cost_volume_flow_net.py:11-15: Conv2d(bias=True) followed by
+ * LeakyReLU(0.1)); the convolution itself stays on cuDNN (out of scope), called without bias.
+ *   fwd: y[b,c,:] = lrelu(x[b,c,:] + bias[c]) in one pass (y may alias x).
+ *   bwd: grad_x = grad_y * (y > 0 ? 1 : slope), grad_bias[c] = sum over b and pixels of grad_x (zeroed inside), one pass.
+ * ------------------------------------------------------------------------------------------- */
+int ocf_bias_lrelu_fwd(const float* x, const float* bias, float* y, int B, int C, long long HW, float slope, ocf_stream_t stream);
+int ocf_bias_lrelu_bwd(const float* grad_y, const float* y, float* grad_x, float* grad_bias, int B, int C, long long HW, float slope,
+                       ocf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Bilinear resampling, align_corners=True.  Replaces the two F.interpolate calls either side of the hot path:
  *   F.interpolate(flow2, scale_factor=4, mode='bilinear', align_corners=True) * 20   (cost_volume_flow_net.py:245; mul = 20)
  *   F.interpolate(img1, scale_factor=0.25, mode='bilinear', align_corners=True)      (models/model.py:396)

@@ -30,6 +30,8 @@ SIGNATURES = {
     "ocf_normalize_bwd": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_s],
     "ocf_resize_bilinear_fwd": [c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_s],
     "ocf_resize_bilinear_bwd": [c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_s],
+    "ocf_bias_lrelu_fwd": [c_f, c_f, c_f, c_i, c_i, c_ll, c_fl, c_s],
+    "ocf_bias_lrelu_bwd": [c_f, c_f, c_f, c_f, c_i, c_i, c_ll, c_fl, c_s],
     "ocf_warp_fwd": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_s],
     "ocf_warp_bwd": [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_fl, c_s],
     "ocf_range_map": [c_f, c_f, c_f, c_i, c_i, c_i, c_s],
@@ -90,7 +92,7 @@ def error_string(code):
 # launch counter: every successful C-ABI call that enqueues kernels bumps it (bench.py's gpu_launches)
 launch_count = 0
 KERNELS_PER_CALL = {
-    "ocf_corr_fwd": 1, "ocf_corr_bwd": 1, "ocf_normalize_stats": 1, "ocf_normalize_apply": 1, "ocf_corr_fwd_strided": 1, "ocf_level_corr_fwd": 1, "ocf_level_corr_bwd": 1, "ocf_normalize_fwd": 2, "ocf_normalize_bwd": 2, "ocf_warp_fwd": 1, "ocf_resize_bilinear_fwd": 1, "ocf_resize_bilinear_bwd": 1,
+    "ocf_corr_fwd": 1, "ocf_corr_bwd": 1, "ocf_normalize_stats": 1, "ocf_normalize_apply": 1, "ocf_corr_fwd_strided": 1, "ocf_level_corr_fwd": 1, "ocf_level_corr_bwd": 1, "ocf_normalize_fwd": 2, "ocf_normalize_bwd": 2, "ocf_warp_fwd": 1, "ocf_bias_lrelu_fwd": 1, "ocf_bias_lrelu_bwd": 1, "ocf_resize_bilinear_fwd": 1, "ocf_resize_bilinear_bwd": 1,
     "ocf_warp_bwd": 1, "ocf_range_map": 1, "ocf_flow_to_warp": 1, "ocf_robust_l1_fwd": 1, "ocf_robust_l1_bwd": 1,
     "ocf_photometric_fwd": 1, "ocf_photometric_bwd": 1, "ocf_smooth_fwd": 1, "ocf_smooth_bwd": 1, "ocf_gradient": 1,
     "ocf_occ_photo_fused": 1, "ocf_pair_loss": 1, "ocf_ssim_fwd": 1, "ocf_ssim_bwd": 1, "ocf_census_fwd": 1, "ocf_census_bwd": 1, "ocf_flow_metrics": 1, "ocf_pack_pairs": 1, "ocf_pack_occ": 1,

@@ -35,8 +35,23 @@ _WARP_SCALE = {5: 0.625, 4: 1.25, 3: 2.5, 2: 5.0}
 _CONTEXT = ((128, 1), (128, 2), (128, 4), (96, 8), (64, 16), (32, 1))  # (out channels, dilation)
 
 
+class _ConvBlock(nn.Sequential):
+    """nn.Sequential(Conv2d(bias=True), LeakyReLU(0.1)) -- the reference's `conv` helper (cost_volume_flow_net.py:11-15), same
+    parameter names ('<block>.0.weight', '<block>.0.bias').  On CUDA the convolution runs without its bias and the bias add +
+    LeakyReLU are ONE in-place pass (ops.bias_leaky_relu_; backward: leaky_relu' and the bias-gradient sum in one pass) instead of
+    ATen's bias-add kernel + LeakyReLU kernel (+ leaky_relu_backward + a separate reduction in the backward)."""
+    fused_epilogue = os.environ.get("OCF_FUSED_CONV_EPILOGUE", "1") == "1"
+
+    def forward(self, x):
+        conv = self[0]
+        if not (self.fused_epilogue and x.is_cuda and x.dtype == torch.float32):
+            return super().forward(x)
+        y = nn.functional.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+        return ops.bias_leaky_relu_(y, conv.bias, self[1].negative_slope)
+
+
 def _conv_block(cin, cout, stride=1, dilation=1):
-    return nn.Sequential(nn.Conv2d(cin, cout, 3, stride=stride, padding=dilation, dilation=dilation, bias=True), nn.LeakyReLU(0.1))
+    return _ConvBlock(nn.Conv2d(cin, cout, 3, stride=stride, padding=dilation, dilation=dilation, bias=True), nn.LeakyReLU(0.1))
 
 
 class FlowNetCV(nn.Module):

@@ -357,6 +357,44 @@ def resize_bilinear(x, size=None, scale_factor=None, mul=1.0):
 
 
 # -------------------------------------------------------------------------------------------------
+# bias + LeakyReLU epilogue of the convolution blocks (cost_volume_flow_net.py:11-15)
+# -------------------------------------------------------------------------------------------------
+class _BiasLeakyReLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, bias, slope):
+        B, C, H, W = x.shape
+        # in place: x is the fresh output of the (bias-free) convolution, whose backward does not need it
+        with torch.cuda.device_of(x):
+            _lib.call("ocf_bias_lrelu_fwd", _p(x), _p(bias), _p(x), B, C, H * W, float(slope), _stream())
+        ctx.slope = float(slope)
+        ctx.mark_dirty(x)
+        ctx.save_for_backward(x)
+        return x
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        B, C, H, W = y.shape
+        g = g.contiguous()
+        dx = torch.empty_like(y)
+        dbias = torch.empty(C, device=y.device, dtype=torch.float32)
+        with torch.cuda.device_of(y):
+            _lib.call("ocf_bias_lrelu_bwd", _p(g), _p(y), _p(dx), _p(dbias), B, C, H * W, ctx.slope, _stream())
+        return dx, dbias, None
+
+
+def bias_leaky_relu_(x, bias, negative_slope=0.1):
+    """lrelu(x + bias[None, :, None, None]) computed in place on x (the output of a bias-free convolution)."""
+    x = _req(x, "x", 4)
+    bias = _req(bias, "bias", 1)
+    if bias.shape[0] != x.shape[1]:
+        raise ValueError("bias must have one entry per channel")
+    if x.numel() == 0:
+        return x
+    return _BiasLeakyReLU.apply(x, bias, float(negative_slope))
+
+
+# -------------------------------------------------------------------------------------------------
 # range map / occlusion  (forward only: the reference calls it under no_grad, models/model.py:381-391)
 # -------------------------------------------------------------------------------------------------
 def range_map(flow, with_occlusion=False):

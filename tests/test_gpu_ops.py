@@ -344,3 +344,24 @@ def test_empty_batches_return_empty_results_like_the_reference():
     assert ops.range_map(fl).shape == (0, 1, 6, 7)
     ref = O.cost_volume(torch.zeros(0, 8, 6, 7), torch.zeros(0, 8, 6, 7), 4)
     assert ref.shape == cv.shape
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 24, 32), (3, 5, 7, 9), (1, 196, 6, 8), (8, 32, 96, 128)])
+def test_bias_leaky_relu_epilogue_equals_the_aten_ops(shape):
+    """ops.bias_leaky_relu_ (the FlowNetCV conv-block epilogue, cost_volume_flow_net.py:11-15) against conv-bias-add + LeakyReLU as
+    ATen runs them: bit-identical forward, gradients to the input (exact) and to the bias (summation order differs)."""
+    from ocflow_b200 import ops
+
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g).cuda()
+    b = torch.randn(shape[1], generator=g).cuda()
+    cot = torch.randn(*shape, generator=g).cuda()
+    x1, b1 = x.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = torch.nn.functional.leaky_relu(x1 + b1[None, :, None, None], 0.1)
+    gx_ref, gb_ref = torch.autograd.grad((ref * cot).sum(), (x1, b1))
+    x2, b2 = x.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    out = ops.bias_leaky_relu_(x2 * 1.0, b2, 0.1)          # x2 * 1.0: a fresh tensor the op may overwrite, like a convolution output
+    assert torch.equal(out, ref)
+    gx, gb = torch.autograd.grad((out * cot).sum(), (x2, b2))
+    assert torch.equal(gx, gx_ref)
+    assert_close(gb, gb_ref, 1e-5, "bias gradient")
