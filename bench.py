@@ -591,6 +591,8 @@ def main():
                 k, v["us"], v["gbs"], v["gbs"] / peak, ref["us"], ref["us"] / v["us"]))
         return
     torch.backends.cudnn.benchmark = True
+    if os.environ.get("OCF_CUDNN_BENCH_LIMIT"):     # developer knob: how many algorithms the cuDNN autotuner tries (torch default 10, 0 = all)
+        torch.backends.cudnn.benchmark_limit = int(os.environ["OCF_CUDNN_BENCH_LIMIT"])
     torch.backends.cudnn.allow_tf32 = bool(args.tf32)
     torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
     B, H, W = args.batch, args.height, args.width
