@@ -81,7 +81,7 @@ class TrainStep:
         net = getattr(model, "flow_pred", None)
         late = list(net.encoder_parameters()) if hasattr(net, "encoder_parameters") else []
         self.grads = FlatGrads(model.parameters(), late=late)
-        self._overlap = bool(late) and hasattr(net, "decoder_grads_done_hook")
+        self._overlap = bool(late) and hasattr(net, "decoder_grads_done_hook") and os.environ.get("OCF_EARLY_ALLREDUCE", "1") == "1"
         self._early_done = False
         self._side = None
         if self._overlap:
@@ -95,6 +95,8 @@ class TrainStep:
         self.static_loss = None
 
     def _world(self):
+        if os.environ.get("OCF_DIAG_NO_ALLREDUCE") == "1":   # diagnosis only: ranks run as independent replicas (slowest-GPU step time)
+            return 1
         return dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
 
     def _reduce_early(self):
