@@ -472,16 +472,23 @@ def live_kernel_times(step, batch, torch, height, reps=3):
             return "%s_L%d" % (short, level(ints[H_INDEX[name]]))
         return short
 
-    step._eager(batch)
-    torch.cuda.synchronize()
-    _lib.live_timer = []
+    # single-stream decodes for this pass: with the swapped pair's decode on its side stream the events around one call also
+    # see whatever the other stream's convolutions are doing on the same SMs (first round-2 lines: corr_fwd_L2 108 us "live"
+    # against 28 us alone), so the numbers would not be the kernel's own
+    from ocflow_b200.flow_net_cv import FlowNetCV
+    overlap = FlowNetCV.overlap_decodes
+    FlowNetCV.overlap_decodes = False
     try:
+        step._eager(batch)
+        torch.cuda.synchronize()
+        _lib.live_timer = []
         for _ in range(reps):
             step._eager(batch)
         torch.cuda.synchronize()
         rec = _lib.live_timer
     finally:
         _lib.live_timer = None
+        FlowNetCV.overlap_decodes = overlap
     agg = {}
     for name, ints, e0, e1 in rec:
         agg.setdefault(classify(name, ints), []).append(e0.elapsed_time(e1) * 1e3)
@@ -744,7 +751,7 @@ def main():
                             "peak_source": peak_src, "launch_us": us,
                             "algorithmic_bytes": kt[dom]["bytes"], "launches_per_step": live[dom][1],
                             "timing": ("mean over the launches of 3 eager training steps, CUDA events around each C-ABI call on its "
-                                       "launching stream (inputs as the step leaves them in L2)") if world == 1 else
+                                       "launching stream (inputs as the step leaves them in L2; decodes on one stream for this pass)") if world == 1 else
                                       "kernel alone on the step's shapes, L2 flushed before every launch",
                             "isolated_l2_flushed": {"launch_us": kt[dom]["us"], "achieved": kt[dom]["gbs"], "frac": kt[dom]["gbs"] / peak}}
         line["kernels"] = {k: {"us": round(v["us"], 2), "gbs": round(v["gbs"], 1), "frac": round(v["gbs"] / peak, 3),
