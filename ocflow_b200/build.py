@@ -18,7 +18,7 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libocflow_b200.so")
 STAMP = os.path.join(PKG, ".libocflow_b200.stamp")
-SOURCES = ["corr.cu", "corr_tc.cu", "corr10.cu", "level.cu", "warp.cu", "resample.cu", "conv_glue.cu", "loss.cu", "normalize.cu", "ssim.cu", "census.cu", "metrics.cu",
+SOURCES = ["corr.cu", "corr_tc.cu", "level.cu", "warp.cu", "resample.cu", "conv_glue.cu", "loss.cu", "normalize.cu", "ssim.cu", "census.cu", "metrics.cu",
            "pack.cu", "abi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-DOCF_BUILD_SM=100",
               "-Xcompiler", "-fPIC"]

@@ -46,6 +46,14 @@ namespace cg = cooperative_groups;
 #ifndef OCF_FWD_CTAS_PER_SM
 #define OCF_FWD_CTAS_PER_SM 1
 #endif
+// tiled backward, TMA path: specialised cross-dy reduction (32-bit indices, packed adds); 0 = the general loop (A/B builds)
+#ifndef OCF_BWD_FASTRED
+#define OCF_BWD_FASTRED 1
+#endif
+// tiled backward, TMA path: one mbarrier per coefficient box (a warp lifts as soon as its own box has landed); 0 = one for all
+#ifndef OCF_BWD_GBAR_PER_BOX
+#define OCF_BWD_GBAR_PER_BOX 1
+#endif
 
 #ifdef OCF_TIMELINE
 // developer builds only (tools/timeline.py): per-CTA globaltimer stamps of the persistent kernels
@@ -58,13 +66,25 @@ __device__ __forceinline__ unsigned long long ocf_now() {
 #define OCF_TL(slot) do { if (threadIdx.x == 0 && blockIdx.x < 1024) ocf_tl[blockIdx.x * 16 + (slot)] = ocf_now(); } while (0)
 #define OCF_TLX(cond, slot) do { if ((cond) && blockIdx.x < 1024) ocf_tl[blockIdx.x * 16 + (slot)] = ocf_now(); } while (0)
 #define OCF_TL_SM() do { if (threadIdx.x == 0 && blockIdx.x < 1024) { unsigned sm; asm("mov.u32 %0, %smid;" : "=r"(sm)); ocf_tl[blockIdx.x * 16 + 15] = sm; } } while (0)
+// 3-D grids (tiled backward): rows indexed by the linear block id
+#define OCF_TLB(cond, slot) do { const unsigned l_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z); \
+    if ((cond) && l_ < 1024) ocf_tl[l_ * 16 + (slot)] = ocf_now(); } while (0)
+#define OCF_TLB_VAL(cond, slot, val) do { const unsigned l_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z); \
+    if ((cond) && l_ < 1024) ocf_tl[l_ * 16 + (slot)] = (unsigned long long)(val); } while (0)
 extern "C" int ocf_debug_timeline(unsigned long long* host, int n) {
+  if (host == nullptr) {   // reset (between two settings probed in one process)
+    void* p = nullptr;
+    cudaError_t e = cudaGetSymbolAddress(&p, ocf_tl);
+    return e != cudaSuccess ? (int)e : (int)cudaMemset(p, 0, sizeof(ocf_tl));
+  }
   return (int)cudaMemcpyFromSymbol(host, ocf_tl, sizeof(unsigned long long) * n);
 }
 #else
 #define OCF_TL(slot) do { } while (0)
 #define OCF_TLX(cond, slot) do { } while (0)
 #define OCF_TL_SM() do { } while (0)
+#define OCF_TLB(cond, slot) do { } while (0)
+#define OCF_TLB_VAL(cond, slot, val) do { } while (0)
 #endif
 
 namespace {
@@ -143,6 +163,12 @@ __device__ __forceinline__ void tma_load_4d(float* smem_dst, const CUtensorMap* 
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(c), "r"(b)
       : "memory");
 }
+// the same box, only as far as the L2 (a hint: no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int x, int y, int c, int b) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(c), "r"(b)
+               : "memory");
+}
 // dense [c][y][x] box in shared memory -> one 4-D box {x, y, c, b} of an NCHW fp32 tensor (elements outside the tensor are dropped)
 __device__ __forceinline__ void tma_store_4d(const float* smem_src, const CUtensorMap* map, int x, int y, int c, int b) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
@@ -166,6 +192,12 @@ __device__ __forceinline__ u64 pack2(float lo, float hi) {
 }
 __device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ void ffma2(u64& d, u64 a, u64 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); }
+__device__ __forceinline__ void fadd2(u64& d, u64 a) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(d) : "l"(a)); }
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b) {
+  u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
 
 template <int THREADS>
 __device__ __forceinline__ void consumer_bar_sync() {  // named barrier 1: the compute warps only (the producer warp is not part)
@@ -697,27 +729,42 @@ corr_fwd_generic(const float* __restrict__ f1, const float* __restrict__ f2, flo
 // ---- backward -----------------------------------------------------------------------------------
 // mode 0: dout = d f1, fo = f2 ; mode 1: dout = d f2, fo = f1.
 // blockIdx.z = (b * nmodes + slot) * ksplit + channel slice.
-// GDIRECT (TMA staging only, experiment): the 81 coefficient planes go global -> registers with 128-bit loads instead of through a
-// TMA-staged shared-memory copy, so that the feature ring starts filling at kernel entry.  Measured slower, see the launcher.
-template <class T, int CR, int STG, bool GDIRECT = false>
+// GD (TMA staging only, experiments): 1 = the 81 coefficient planes go global -> registers with 128-bit loads instead of through
+// a TMA-staged shared-memory copy, so that the feature ring starts filling at kernel entry; 2 = the same for mode 0 only (d f1:
+// aligned planes, 18 loads straight into their final registers), mode 1 keeps the staged lift (unaligned: 27 loads through 12
+// temporaries per displacement).  pf_stride > 0: the producer thread asks the TMA unit to PREFETCH INTO L2 the coefficient
+// boxes and the first feature boxes of the CTA pf_stride linear block ids ahead (the one that will take over a slot of this
+// wave), once its own ring is full -- the next wave's prologue then reads L2 instead of DRAM.  3 = EARLY first stage (use with a
+// CC = 4 tile): the coefficient boxes are 40 instead of 44 floats wide (2-way bank conflicts in the one-off lift), which leaves
+// room for ONE feature stage next to the staging area, so the first feature box travels together with the coefficients instead
+// of one more memory round trip behind them; the other stages and the reduction buffer alias the staging area as before.
+// Measured (see the launcher): only the prefetch pays; it is on by default, GD stays 0.
+template <class T, int CR, int STG, int GD = 0>
 __global__ void __launch_bounds__(Threads<T, STG>::value, 2)
 corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
                const __grid_constant__ CUtensorMap mapg, const float* __restrict__ g,
                const float* __restrict__ oact, const unsigned char* __restrict__ mask, const float* __restrict__ f1,
                const float* __restrict__ f2, float* __restrict__ df1,
                float* __restrict__ df2, int C, int H, int W, long long g_bstride, long long a_bstride, float inv_c, float slope,
-               int nmodes, int first_mode, int ksplit, long long f1_bstride, long long f2_bstride) {
+               int nmodes, int first_mode, int ksplit, long long f1_bstride, long long f2_bstride, int pf_stride) {
   constexpr int D = T::D, PX = T::PX, ND = T::ND, TH = T::TH, TW = T::TW, CC = T::CC, STAGES = T::STAGES;
   constexpr int S1 = T::S1, S2 = T::S2, F2H = T::F2H, F2W = T::F2W, WIN = T::WIN;
   constexpr bool TMA = STG == STG_TMA;
   constexpr bool VEC = STG != STG_ASYNC4;
   static_assert(CC % CR == 0, "CC must be a multiple of CR");
   extern __shared__ __align__(128) float smem[];
-  __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES], g_bar, gdone_bar;
-  float* red = smem + STAGES * T::F2_STAGE;  // [NDY][CR][TH][S1]
+  __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES], g_bar[T::ND], gdone_bar;   // g_bar: one per dy box
+  constexpr bool EARLY = GD == 3;
+  static_assert(!EARLY || (STG == STG_TMA && T::NGY == 1), "the early first stage is a TMA-path layout");
+  float* red = smem + (EARLY ? STAGES - 1 : STAGES) * T::F2_STAGE;  // [NDY][CR][TH][S1]
   // TMA variant: the 81 coefficient planes of the tile are staged through shared memory first (one {GW, TH, ND} box per
   // dy-warp, GW == 12 mod 32 floats so the 128-bit reads are conflict-free); the area is then reused by the ring + red.
-  constexpr int GW = T::S2, BOXG = ND * TH * GW;
+  constexpr int GW = EARLY ? T::F2W : T::S2, BOXG = ND * TH * GW;
+  // ring stage s: EARLY keeps stage 0 behind the staging area (never aliased), stages 1.. at the bottom
+  auto stage_base = [&](int s) -> float* {
+    if constexpr (EARLY) return s == 0 ? smem + ND * BOXG : smem + (s - 1) * T::F2_STAGE;
+    else return smem + s * T::F2_STAGE;
+  };
 
   const int tid = threadIdx.x;
   const int lane = tid % T::LANES;
@@ -731,6 +778,7 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
   static_assert(T::NGY == 1 || STG != STG_TMA, "the TMA-staged backward handles all displacements in one CTA");
   const int b = zz / nmodes;
   const int mode = first_mode + (zz - b * nmodes);
+  const bool direct = GD == 1 || (GD == 2 && mode == 0);   // compile-time constant unless GD == 2
   const ChunkRange cr = chunk_range(C, CC, ksplit, ks);
   const int nchunks = cr.count;
   float* dout = (mode == 0 ? df1 : df2) + (size_t)b * C * H * W;
@@ -739,10 +787,16 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
 
   float G[ND][PX];  // 81 per-pixel coefficients of this thread's dy row, kept in registers for the whole kernel
   if constexpr (TMA) {
+    OCF_TLB(tid == 0, 0);
+    OCF_TLB_VAL(tid == 0, 5, mode + 1);
+#ifdef OCF_TIMELINE
+    if (tid == 0) { unsigned sm_; asm("mov.u32 %0, %smid;" : "=r"(sm_)); OCF_TLB_VAL(true, 15, sm_); }
+#endif
     if (tid == 0) {
 #pragma unroll
       for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ND); }
-      mbar_init(&g_bar, 1);
+#pragma unroll
+      for (int w = 0; w < ND; ++w) mbar_init(&g_bar[w], 1);
       mbar_init(&gdone_bar, ND);
       mbar_fence_init();
     }
@@ -750,23 +804,51 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
     const bool has_act = oact != nullptr || mask != nullptr;
     if (dyi == ND) {
       if (lane == 0) {
-        if constexpr (!GDIRECT) {
+        if (!direct) {
         // coefficient boxes: mode 0 -> planes dy*ND.. at (y0, x0) ; mode 1 -> planes (2D-dy)*ND.. at (y0+dy-D, x0-D)
-        constexpr unsigned GBYTES = sizeof(float) * ND * BOXG;
-        mbar_expect_tx(&g_bar, GBYTES);
+        // (one barrier per box: a warp lifts its nine planes as soon as ITS box has landed, while the later boxes are still
+        // on their way, instead of all nine warps waiting for the last byte of the 114 KB)
+        constexpr unsigned GBYTES = sizeof(float) * BOXG;
         for (int w = 0; w < ND; ++w) {
           const int plane0 = mode == 0 ? w * ND : (2 * D - w) * ND;
-          tma_load_4d(smem + w * BOXG, &mapg, &g_bar, mode == 0 ? x0 : x0 - D, mode == 0 ? y0 : y0 + w - D, plane0, b);
+          unsigned long long* gb_ = &g_bar[OCF_BWD_GBAR_PER_BOX ? w : 0];
+          if (OCF_BWD_GBAR_PER_BOX || w == 0) mbar_expect_tx(gb_, OCF_BWD_GBAR_PER_BOX ? GBYTES : GBYTES * ND);
+          tma_load_4d(smem + w * BOXG, &mapg, gb_, mode == 0 ? x0 : x0 - D, mode == 0 ? y0 : y0 + w - D, plane0, b);
+        }
+        if constexpr (EARLY) {
+          if (nchunks > 0) {   // the first feature box rides along with the coefficients (its stage is not part of the staging area)
+            mbar_expect_tx(&full_bar[0], (unsigned)sizeof(float) * T::F2_STAGE);
+            tma_load_4d(stage_base(0), mode == 0 ? &map2 : &map1, &full_bar[0], x0 - D, y0 - D, cr.begin * CC, b);
+          }
         }
         mbar_wait(&gdone_bar, 0);  // every warp has lifted its coefficients out of the staging area: feed the feature ring
         }
         constexpr unsigned BYTES = sizeof(float) * T::F2_STAGE;
         const CUtensorMap* map = mode == 0 ? &map2 : &map1;  // the OTHER feature
-        for (int i = 0; i < nchunks; ++i) {
+        const int pf_at = min(nchunks, STAGES) - 1;          // the ring is full after this chunk: time to think of the next wave
+        for (int i = EARLY ? 1 : 0; i < nchunks; ++i) {
           const int s = i % STAGES;
           if (i >= STAGES) mbar_wait(&empty_bar[s], ((i / STAGES) - 1) & 1);
           mbar_expect_tx(&full_bar[s], BYTES);
-          tma_load_4d(smem + s * T::F2_STAGE, map, &full_bar[s], x0 - D, y0 - D, (cr.begin + i) * CC, b);
+          tma_load_4d(stage_base(s), map, &full_bar[s], x0 - D, y0 - D, (cr.begin + i) * CC, b);
+          if (pf_stride > 0 && i == pf_at) {
+            // L2 prefetch for the CTA pf_stride linear ids ahead: same decode as above, hints only (nothing waits on them)
+            const long long lin = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z) + pf_stride;
+            const long long per_z = (long long)gridDim.x * gridDim.y;
+            if (lin < per_z * gridDim.z) {
+              const int nz = (int)(lin / per_z), rem = (int)(lin - nz * per_z);
+              const int nyb = rem / (int)gridDim.x, nxb = rem - nyb * (int)gridDim.x;
+              const int nzz0 = nz / ksplit, nks = nz - nzz0 * ksplit;
+              const int nzz = nzz0 / T::NGY;
+              const int nb = nzz / nmodes, nmode = first_mode + (nzz - nb * nmodes);
+              const int nx0 = nxb * TW, ny0 = nyb * TH;
+              for (int w = 0; w < ND; ++w)
+                tma_prefetch_4d(&mapg, nmode == 0 ? nx0 : nx0 - D, nmode == 0 ? ny0 : ny0 + w - D, nmode == 0 ? w * ND : (2 * D - w) * ND, nb);
+              const ChunkRange ncr = chunk_range(C, CC, ksplit, nks);
+              const CUtensorMap* nmap = nmode == 0 ? &map2 : &map1;
+              for (int j = 0; j < min(ncr.count, STAGES); ++j) tma_prefetch_4d(nmap, nx0 - D, ny0 - D, (ncr.begin + j) * CC, nb);
+            }
+          }
         }
       }
       return;  // the producer warp takes no part in the compute-warp barriers below
@@ -830,7 +912,7 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
         }
       }
     }
-    if constexpr (GDIRECT) {
+    if (direct) {
       // W % 4 == 0 on this path: an aligned group of 4 columns is entirely inside or entirely outside the row
       const float* gp = g + gb;
       const int xs = x0 + tx * PX;
@@ -868,7 +950,8 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
       }
     } else {
     const float* gw = smem + dyi * BOXG + ty * GW + tx * PX;
-    mbar_wait(&g_bar, 0);
+    mbar_wait(&g_bar[OCF_BWD_GBAR_PER_BOX ? dyi : 0], 0);
+    OCF_TLB(tid == 0, 1);
     if (mode == 0) {
 #pragma unroll
       for (int dx = 0; dx < ND; ++dx) {
@@ -893,6 +976,9 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&gdone_bar);
+    // EARLY: the first feature stage is already there, so nothing else keeps a fast warp from writing its partial sums into
+    // the reduction buffer -- which aliases the boxes slower warps are still lifting
+    if constexpr (EARLY) mbar_wait(&gdone_bar, 0);
     }
     if (has_act) {
 #pragma unroll
@@ -901,6 +987,7 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
         for (int p = 0; p < PX; ++p)
           if (!((mbits[dx / 3] >> ((dx % 3) * PX + p)) & 1u)) G[dx][p] *= slope;
     }
+    OCF_TLB(tid == 0, 2);
   }
   const float* fo = (mode == 0 ? f2 + (size_t)b * (f2_bstride ? (size_t)f2_bstride : (size_t)C * H * W)
                                : f1 + (size_t)b * (f1_bstride ? (size_t)f1_bstride : (size_t)C * H * W));
@@ -943,6 +1030,7 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
     const int s = i % STAGES;
     if constexpr (TMA) {
       mbar_wait(&full_bar[s], (i / STAGES) & 1);
+      OCF_TLB(tid == 0 && i == 0, 3);
     } else {
       cp_async_wait<STAGES - 2>();
       __syncthreads();
@@ -950,7 +1038,7 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
       cp_async_commit();
     }
     const int c0 = (cr.begin + i) * CC;
-    const float* pw = smem + s * T::F2_STAGE + (ty + dyi) * S2 + tx * PX;
+    const float* pw = stage_base(s) + (ty + dyi) * S2 + tx * PX;
 #pragma unroll 1
     for (int r0 = 0; r0 < CC; r0 += CR) {
       if (c0 + r0 >= C) break;  // uniform across the block
@@ -979,6 +1067,36 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
       if constexpr (TMA) consumer_bar_sync<T::THREADS>(); else __syncthreads();
       // cross-dy reduction: CR*TH*TW/4 float4 outputs
       constexpr int OUT4 = CR * TH * TW / 4;
+      if constexpr (TMA && T::NGY == 1 && OUT4 <= T::THREADS && OCF_BWD_FASTRED) {
+        // TMA path (W % 4 == 0, dense 16-byte aligned outputs): one float4 per thread, 32-bit index math (the compiler
+        // re-derives the indices in every group -- the 96 registers are all taken during the compute phase -- and did so in
+        // 64 bits: ~50 of the ~105 instructions of this phase) and packed adds (add.f32x2: 16 instead of 32): 105 -> 73
+        // instructions.  Same order of additions as the general form below (bit-identical results).
+        if (tid < OUT4) {
+          constexpr int X4 = TW / 4;
+          const int x4 = tid % X4, ry = (tid / X4) % TH, c = tid / (X4 * TH);
+          const float* rp = red + (c * TH + ry) * S1 + x4 * 4;
+          float4 v = *reinterpret_cast<const float4*>(rp);
+          u64 s01 = pack2(v.x, v.y), s23 = pack2(v.z, v.w);
+#pragma unroll
+          for (int k = 1; k < T::NDY; ++k) {
+            v = *reinterpret_cast<const float4*>(rp + k * CR * TH * S1);
+            fadd2(s01, pack2(v.x, v.y));
+            fadd2(s23, pack2(v.z, v.w));
+          }
+          const int ch = c0 + r0 + c, y = y0 + ry, x = x0 + x4 * 4;
+          if (ch < C && y < H && x < W) {
+            const u64 ic = pack2(inv_c, inv_c);
+            float4 o4;
+            unpack2(fmul2(s01, ic), o4.x, o4.y);
+            unpack2(fmul2(s23, ic), o4.z, o4.w);
+            // C * H * W < 2^31 (checked by the launcher).  (Measured: parking the base pointer in shared memory -- the compiler
+            // re-derives the 64-bit b * C * H * W in every group -- saves 14 instructions and is 4 % SLOWER: an LDS.64 in front of
+            // a generic store on the critical path to the barrier.)
+            *reinterpret_cast<float4*>(dout + (unsigned)((ch * H + y) * W + x)) = o4;
+          }
+        }
+      } else
       for (int j = tid; j < OUT4; j += T::THREADS) {
         const int x4 = j % (TW / 4), row = j / (TW / 4);  // row = c*TH + ry
         const int c = row / TH, ry = row - c * TH;
@@ -1010,6 +1128,7 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
         }
       }
       if constexpr (TMA) consumer_bar_sync<T::THREADS>(); else __syncthreads();
+      OCF_TLB(TMA && tid == 0 && i == 0 && r0 == 0, 4);
     }
     if constexpr (TMA) {
       // the last consumer barrier above ordered every warp's reads of this stage: one arrival per warp frees it
@@ -1017,6 +1136,7 @@ corr_bwd_tiled(const __grid_constant__ CUtensorMap map1, const __grid_constant__
     }
   }
   if constexpr (!TMA) cp_async_wait<0>();
+  OCF_TLB(TMA && tid == 0, 14);
 }
 
 // ---- backward, channel-split persistent form (d = 4, TMA, sign bitmask or no activation) ------------------------------
@@ -1258,6 +1378,7 @@ corr_bwd_generic(const float* __restrict__ g, const float* __restrict__ oact, co
 using Tile4 = CorrTile<4, 8, 4, 8, 8, 3>;
 // d = 10: 4 x 32 pixel tile, thread = 4 pixels x 21 horizontal displacements (84 accumulators), 7 dy-warps per CTA, 3 CTAs per tile
 using Tile10 = CorrTile<10, 4, 8, 4, 8, 3, 7, 128>;
+using Tile4E = CorrTile<4, 8, 4, 8, 4, 6>;   // backward with the early first stage (GD = 3): 4-channel stages, 6 of them
 #ifndef OCF_FWD_STAGES
 #define OCF_FWD_STAGES 6
 #endif
@@ -1534,12 +1655,30 @@ int ocf_corr_bwd_impl(const float* grad_out, const float* out_act, const float* 
     const long long abs_ = act_bstride ? act_bstride : nd * nd * H * W;
     bool tma = vec && ocf_aligned16(grad_out) && (out_act == nullptr || ocf_aligned16(out_act)) && (gbs % 4 == 0) && (abs_ % 4 == 0);
     tma = tma && (f1_bstride % 4 == 0) && (f2_bstride % 4 == 0);
+    tma = tma && (long long)C * H * W < (1LL << 31);   // 32-bit element offsets inside one batch item (the reduction's stores)
     tma = tma && make_map(&m1, f1, B, C, H, W, T::S2, T::F2H, T::CC, f1_bstride) && make_map(&m2, f2, B, C, H, W, T::S2, T::F2H, T::CC, f2_bstride) &&
           make_map(&mg, grad_out, B, (int)(nd * nd), H, W, T::S2, T::TH, T::ND, gbs);
     // developer knob (A/B runs): OCF_BWD_GDIRECT=1 loads the coefficients global -> registers.  Measured: SLOWER (L2 level 70.3 vs
     // 61.3 us, L3 43.0 vs 38.8): with 96 registers per thread only ~5 of the 18-24 128-bit loads are in flight, so the lift costs
     // several L2 round trips instead of one TMA round trip.  The staged form stays the default.
-    static const int gdirect = []() { const char* e = getenv("OCF_BWD_GDIRECT"); return e ? atoi(e) : 0; }();
+    // OCF_BWD_GDIRECT=2: direct for mode 0 only; =3: early first stage (4-channel stages, 40-float boxes).  OCF_BWD_PREFETCH (default 1):
+    // L2 prefetch of the next wave's boxes (stride = the 2 x 148 resident CTAs of a wave; any other positive value is taken as the stride
+    // itself; 0 = off).  OCF_KNOBS_DYNAMIC=1 re-reads both on every call (A/B probes inside one process: tools/probe_bwd_knobs.py);
+    // otherwise they are read once.  Measured with the per-CTA timeline of tools/timeline.py (profiles/r2_corr_bwd_timeline.txt; L2
+    // level 8x32x96x128, times per CTA): 17.4-17.9 us = 3.0-4.2 us until the coefficient boxes have landed + 0.6 lift + 1.2-1.4 first
+    // feature stage + 10-10.5 main loop (7.6 when the CTA is alone on its SM); three generations of CTAs per slot.
+    //   prefetch:      later-wave boxes land after 2.1 instead of 3.0 us, first stage after 0.7 instead of 1.4: kernel span 55.9 -> 53.6 us,
+    //                  call 61.4 -> 59.4 us (8x32x188x620: 455.7 -> 447.5 us); bit-identical; DEFAULT.
+    //   GDIRECT=2:     65.6 us -- the direct lift of mode 0 takes 4.2-5.8 us (TMA + lift: 3.6-4.8) and this instantiation's main loop 13.3 us.
+    //   GDIRECT=3:     60.4 us, with prefetch 59.4 (= prefetch alone): the first stage is there 1.1-1.3 us earlier, but the 4-channel stages
+    //                  cost the main loop 0.4-0.8 us and the lift has to wait for all nine warps (the reduction buffer aliases the boxes).
+    static const bool knobs_dynamic = getenv("OCF_KNOBS_DYNAMIC") != nullptr;
+    auto knob = [](const char* name) { const char* e = getenv(name); return e ? atoi(e) : 0; };
+    auto knob1 = [](const char* name) { const char* e = getenv(name); return e ? atoi(e) : 1; };   // default ON
+    static const int gdirect0 = knob("OCF_BWD_GDIRECT"), prefetch0 = knob1("OCF_BWD_PREFETCH");
+    const int gdirect = knobs_dynamic ? knob("OCF_BWD_GDIRECT") : gdirect0;
+    const int prefetch = knobs_dynamic ? knob1("OCF_BWD_PREFETCH") : prefetch0;
+    const int pf_stride = prefetch <= 0 ? 0 : (prefetch == 1 ? 2 * OCF_SM_COUNT : prefetch);
     // channel-split persistent form (experiment, OCF_BWD_CS=1): full grids only, sign bitmask or no activation.  Measured SLOWER
     // than the tiled form (L2 level 79 vs 60 us, C = 64: 132 vs 101, C = 128: 228 vs 181): with the coefficients resident in
     // shared memory only 4 feature stages fit, i.e. 4 compute warps per SM -- one per scheduler, issue_active 40 %, fma 29 % -- and
@@ -1553,23 +1692,36 @@ int ocf_corr_bwd_impl(const float* grad_out, const float* out_act, const float* 
       if (int e = set_smem(kernel, csmem)) return e;
       if (int e = launch_kernel(kernel, dim3(OCF_SM_COUNT), (NW + 1) * 32, csmem, s, 1, m1, m2, mg, mask, df1, df2, C, H, W, inv_c, leaky_slope, nmodes,
                                 first, gx, gy, (int)nitems)) return e;
-    } else if (tma && gdirect) {
-      auto kernel = corr_bwd_tiled<T, BWD_CR, STG_TMA, true>;
+    } else if (tma && gdirect == 3) {
+      // early first stage: own tile type (4-channel stages) and maps (40-float coefficient boxes, 4-channel feature boxes)
+      using E = Tile4E;
+      CUtensorMap e1, e2, eg;
+      if (!(make_map(&e1, f1, B, C, H, W, E::S2, E::F2H, E::CC, f1_bstride) && make_map(&e2, f2, B, C, H, W, E::S2, E::F2H, E::CC, f2_bstride) &&
+            make_map(&eg, grad_out, B, (int)(nd * nd), H, W, E::F2W, E::TH, E::ND, gbs))) return OCF_EUNSUPPORTED;
+      const size_t esmem = sizeof(float) * ((size_t)E::ND * E::ND * E::TH * E::F2W + E::F2_STAGE);
+      static_assert(sizeof(float) * ((E::STAGES - 1) * E::F2_STAGE + E::ND * BWD_CR * E::TH * E::S1) <= sizeof(float) * ((size_t)E::ND * E::ND * E::TH * E::F2W),
+                    "ring stages 1.. and the reduction buffer must fit inside the staging area");
+      auto kernel = corr_bwd_tiled<E, BWD_CR, STG_TMA, 3>;
+      if (int e = set_smem(kernel, esmem)) return e;
+      if (int e = launch_kernel(kernel, grid, E::THREADS + 32, esmem, s, 1, e1, e2, eg, grad_out, out_act, mask, f1, f2, df1, df2, C, H, W, g_bstride,
+                                act_bstride, inv_c, leaky_slope, nmodes, first, ks, f1_bstride, f2_bstride, pf_stride)) return e;
+    } else if (tma && gdirect == 1) {
+      auto kernel = corr_bwd_tiled<T, BWD_CR, STG_TMA, 1>;
       if (int e = set_smem(kernel, smem)) return e;
       if (int e = launch_kernel(kernel, grid, T::THREADS + 32, smem, s, 1, m1, m2, mg, grad_out, out_act, mask, f1, f2, df1, df2, C, H, W, g_bstride,
-                                act_bstride, inv_c, leaky_slope, nmodes, first, ks, f1_bstride, f2_bstride)) return e;
+                                act_bstride, inv_c, leaky_slope, nmodes, first, ks, f1_bstride, f2_bstride, pf_stride)) return e;
     } else if (tma) {
       const size_t gstage = sizeof(float) * T::ND * T::ND * T::TH * T::S2;  // coefficient staging, reused by ring + red
       if (gstage > smem) smem = gstage;
-      auto kernel = corr_bwd_tiled<T, BWD_CR, STG_TMA>;
+      auto kernel = gdirect == 2 ? corr_bwd_tiled<T, BWD_CR, STG_TMA, 2> : corr_bwd_tiled<T, BWD_CR, STG_TMA>;
       if (int e = set_smem(kernel, smem)) return e;
       if (int e = launch_kernel(kernel, grid, T::THREADS + 32, smem, s, 1, m1, m2, mg, grad_out, out_act, mask, f1, f2, df1, df2, C, H, W, g_bstride,
-                                act_bstride, inv_c, leaky_slope, nmodes, first, ks, f1_bstride, f2_bstride)) return e;
+                                act_bstride, inv_c, leaky_slope, nmodes, first, ks, f1_bstride, f2_bstride, pf_stride)) return e;
     } else {
       auto kernel = vec ? corr_bwd_tiled<T, BWD_CR, STG_ASYNC16> : corr_bwd_tiled<T, BWD_CR, STG_ASYNC4>;
       if (int e = set_smem(kernel, smem)) return e;
       if (int e = launch_kernel(kernel, grid, T::THREADS, smem, s, 1, m1, m2, mg, grad_out, out_act, mask, f1, f2, df1, df2, C, H, W, g_bstride,
-                                act_bstride, inv_c, leaky_slope, nmodes, first, ks, f1_bstride, f2_bstride)) return e;
+                                act_bstride, inv_c, leaky_slope, nmodes, first, ks, f1_bstride, f2_bstride, 0)) return e;
     }
   } else if (d == 10 && f1_bstride == 0 && f2_bstride == 0) {
     // FlowNetC family: three dy-group CTAs per tile and mode, partial sums accumulated with vector reds into the zeroed outputs
@@ -1591,7 +1743,7 @@ int ocf_corr_bwd_impl(const float* grad_out, const float* out_act, const float* 
     auto kernel = vec ? corr_bwd_tiled<T, BWD_CR, STG_ASYNC16> : corr_bwd_tiled<T, BWD_CR, STG_ASYNC4>;
     if (int er = set_smem(kernel, smem)) return er;
     if (int er = launch_kernel(kernel, grid, T::THREADS, smem, s, 1, m1, m2, mg, grad_out, out_act, mask, f1, f2, df1, df2, C, H, W, g_bstride,
-                               act_bstride, inv_c, leaky_slope, nmodes, first, 1, f1_bstride, f2_bstride)) return er;
+                               act_bstride, inv_c, leaky_slope, nmodes, first, 1, f1_bstride, f2_bstride, 0)) return er;
   } else {
     OCF_REQUIRE(f1_bstride == 0 && f2_bstride == 0, OCF_EUNSUPPORTED);
     dim3 grid((H * W + 127) / 128, C, B);
