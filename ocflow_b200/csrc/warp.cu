@@ -139,6 +139,12 @@ warp_fwd_kernel(const float* __restrict__ img, const float* __restrict__ flow, c
 // instructions per 8 channels -- changes nothing (210 vs 209 us at 8x32x188x620, range map likewise): at that size the scatter is
 // bound by the DRAM traffic of the zero-fill + read-modify-write of d_img (dram_rd 365 MB for 238 MB of inputs), not by the
 // number of red instructions.)
+// (Measured dead end: a third, "interior" path for warps whose lanes all have four valid taps but whose merge plan is not the
+// regular one -- no validity selects, unpredicated loads, the merges and the two east reds predicated per lane: 46 instead of
+// ~105 instructions per sample and channel in the SASS -- changes nothing: 8x32x96x128 on a rough field 53-54 vs 50-51 us, gentle
+// field 37.9 vs 37.9 us, 8x32x188x620 204 vs 209 us.  The same probe shows where the time is: without the d_img scatter the call
+// takes 25.6 us at 8x32x96x128 whatever the field, i.e. two dependent memory round trips (flow -> taps) per short-lived CTA x 5.2
+// generations of CTAs; the scatter adds 12 us on a coherent field and 25-39 us on a rough one.  Instruction count is not it.)
 template <int CB>
 __global__ void __launch_bounds__(WARP_THREADS, 2)
 warp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ img, const float* __restrict__ flow,
