@@ -365,3 +365,20 @@ def test_bias_leaky_relu_epilogue_equals_the_aten_ops(shape):
     gx, gb = torch.autograd.grad((out * cot).sum(), (x2, b2))
     assert torch.equal(gx, gx_ref)
     assert_close(gb, gb_ref, 1e-5, "bias gradient")
+
+
+def test_corr_backward_staging_variants_are_bit_identical():
+    """The developer variants of the tiled correlation backward (coefficients loaded directly, early first feature stage, L2
+    prefetch on / off / other stride) must give the gradients of the default path bit for bit: they only change HOW the
+    operands reach the registers.  Runs tools/probe_bwd_knobs.py in a subprocess (the library decides at its first call
+    whether it re-reads its knobs on every call) on two small geometries, one of them with a partial tile row and C % 8 != 0, and
+    on one with more CTAs than resident slots (768: the prefetch has a next generation to prefetch for)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    proc = subprocess.run([sys.executable, os.path.join(root, "tools", "probe_bwd_knobs.py"), "--reps", "1", "--geoms", "2x32x24x64,3x20x20x36,8x16x96x128"],
+                          capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout + proc.stderr
+    lines = [l for l in proc.stdout.splitlines() if "median" in l]
+    assert len(lines) == 3 * 12, proc.stdout
+    assert all(("bit-identical" in l) or ("reference" in l) for l in lines), proc.stdout
