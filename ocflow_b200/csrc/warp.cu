@@ -348,10 +348,10 @@ flow_to_warp_kernel(const float* __restrict__ flow, float* __restrict__ out, int
 }
 
 // channels per CTA: a multiple of the load batch, small enough that the grid covers the 148 SMs a few times over
-int pick_slab(int C, int HW, int B, int cb) {
+int pick_slab(int C, int HW, int B, int cb, int ctas_per_sm = 8) {
   const long long pix_blocks = ((long long)HW + WARP_THREADS - 1) / WARP_THREADS * B;
   int slab = (C + cb - 1) / cb * cb;
-  while (slab > cb && pix_blocks * ((C + slab - 1) / slab) < 8LL * OCF_SM_COUNT) slab = ((slab / cb + 1) / 2) * cb;
+  while (slab > cb && pix_blocks * ((C + slab - 1) / slab) < (long long)ctas_per_sm * OCF_SM_COUNT) slab = ((slab / cb + 1) / 2) * cb;
   if (slab > 32) slab = 32 / cb * cb;
   return slab < 1 ? 1 : slab;
 }
@@ -401,7 +401,9 @@ extern "C" int ocf_warp_bwd(const float* grad_out, const float* img, const float
   const int HW = H * W;
   const int kcb = warp_cb(false);
   const int cb = (C < 2 || kcb == 1) ? 1 : ((C < 8 || kcb == 4) ? 4 : 8);   // C = 3 (images): one batch of 4, the 4th load repeats channel 2
-  const int slab = pick_slab(C, HW, B, cb);
+  // developer knob (tuning runs): grid target of the backward in CTAs per SM (2 are resident at 128 registers)
+  static const int bwd_target = []() { const char* e = getenv("OCF_WARP_BWD_TARGET"); return e ? atoi(e) : 8; }();
+  const int slab = pick_slab(C, HW, B, cb, bwd_target);
   const int nslabs = (C + slab - 1) / slab;
   OCF_REQUIRE(nslabs <= 65535, OCF_EUNSUPPORTED);
   cudaError_t e;

@@ -20,7 +20,8 @@ ap.add_argument("--shape", default="8,32,188,620")
 ap.add_argument("--kinds", default="zero,gentle,bench,noise")
 ap.add_argument("--ops", default="warp_fwd,warp_bwd,warp_bwd_flow_only,range_map")
 a = ap.parse_args()
-B, C, H, W = (int(v) for v in a.shape.split(","))
+SHAPES = [tuple(int(v) for v in sh.split(",")) for sh in a.shape.split(";")]   # several shapes: "8,32,96,128;8,64,48,64"
+B, C, H, W = SHAPES[0]
 try:
     PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
@@ -61,23 +62,24 @@ def timed(fn, reps=6):
     return statistics.median(ts)
 
 
-n = B * H * W
-img = torch.randn(B, C, H, W, device="cuda", generator=g)
-gout = torch.randn(B, C, H, W, device="cuda", generator=g)
-out = torch.empty_like(img)
-dimg = torch.empty_like(img)
-rm = torch.empty(B, 1, H, W, device="cuda")
-print("shape", (B, C, H, W), "peak", PEAK)
-for kind in a.kinds.split(","):
-    fl = flow_of(kind)
-    dfl = torch.empty_like(fl)
-    cases = {
-        "warp_fwd": (lambda: _lib.call("ocf_warp_fwd", P(img), P(fl), None, P(out), B, C, H, W, 0, 1.0, st), 4 * n * (2 * C + 2)),
-        "warp_bwd": (lambda: _lib.call("ocf_warp_bwd", P(gout), P(img), P(fl), None, P(dimg), P(dfl), None, B, C, H, W, 0, 1.0, st), 4 * n * (3 * C + 4)),
-        "warp_bwd_flow_only": (lambda: _lib.call("ocf_warp_bwd", P(gout), P(img), P(fl), None, None, P(dfl), None, B, C, H, W, 0, 1.0, st), 4 * n * (2 * C + 4)),
-        "range_map": (lambda: _lib.call("ocf_range_map", P(fl), P(rm), None, B, H, W, st), 4 * n * 4),
-    }
-    for name in a.ops.split(","):
-        fn, nbytes = cases[name]
-        t = timed(fn)
-        print("%-8s %-20s %9.1f us  %8.1f GB/s  %.3f of peak" % (kind, name, t * 1e6, nbytes / t / 1e9, nbytes / t / 1e9 / PEAK))
+for B, C, H, W in SHAPES:
+    n = B * H * W
+    img = torch.randn(B, C, H, W, device="cuda", generator=g)
+    gout = torch.randn(B, C, H, W, device="cuda", generator=g)
+    out = torch.empty_like(img)
+    dimg = torch.empty_like(img)
+    rm = torch.empty(B, 1, H, W, device="cuda")
+    print("shape", (B, C, H, W), "peak", PEAK)
+    for kind in a.kinds.split(","):
+        fl = flow_of(kind)
+        dfl = torch.empty_like(fl)
+        cases = {
+            "warp_fwd": (lambda: _lib.call("ocf_warp_fwd", P(img), P(fl), None, P(out), B, C, H, W, 0, 1.0, st), 4 * n * (2 * C + 2)),
+            "warp_bwd": (lambda: _lib.call("ocf_warp_bwd", P(gout), P(img), P(fl), None, P(dimg), P(dfl), None, B, C, H, W, 0, 1.0, st), 4 * n * (3 * C + 4)),
+            "warp_bwd_flow_only": (lambda: _lib.call("ocf_warp_bwd", P(gout), P(img), P(fl), None, None, P(dfl), None, B, C, H, W, 0, 1.0, st), 4 * n * (2 * C + 4)),
+            "range_map": (lambda: _lib.call("ocf_range_map", P(fl), P(rm), None, B, H, W, st), 4 * n * 4),
+        }
+        for name in a.ops.split(","):
+            fn, nbytes = cases[name]
+            t = timed(fn)
+            print("%-8s %-20s %9.1f us  %8.1f GB/s  %.3f of peak" % (kind, name, t * 1e6, nbytes / t / 1e9, nbytes / t / 1e9 / PEAK))
