@@ -619,7 +619,6 @@ extern "C" int ocf_occ_photo_fused(const float* img1, const float* img2, const f
   cudaStream_t s = ocf_cast_stream(stream);
   cudaError_t e = cudaMemsetAsync(sums, 0, 8 * sizeof(double), s);
   if (e != cudaSuccess) return (int)e;
-  const size_t npix = (size_t)B * H * W;
   bool vec = (W % 4 == 0) && ocf_aligned16(img1) && ocf_aligned16(flow);
   const float* opt[5] = {range_map, flow_gt, occ_gt, dflow_unit, warped_out};
   for (const float* p : opt) vec = vec && (p == nullptr || ocf_aligned16(p));
