@@ -208,8 +208,34 @@ def group_data():
     metrics.evaluate_flow(gt[0].permute(1, 2, 0).contiguous(), pr[0].permute(1, 2, 0).contiguous())
 
 
+def group_big():
+    # BASELINE shapes (config-2 L2 level, a ragged KITTI level, the loss level): several generations of CTAs per SM, the
+    # correlation backward's next-generation prefetch, the persistent forward's tile loop.  No oracle here (the parity and
+    # property tests cover these shapes); this group exists for the out-of-bounds guard.
+    for B, C, H, W in ((8, 32, 96, 128), (4, 16, 188, 621), (2, 128, 12, 16)):
+        a, b = leaf(rnd(B, C, H, W)), leaf(rnd(B, C, H, W))
+        run_bwd(ops.cost_volume(a, b, 4, 0.1), a, b)
+        img, flow = leaf(rnd(B, C, H, W)), leaf(rnd(B, 2, H, W, scale=6.0))
+        run_bwd(ops.warp(img, flow, align_corners=False), img, flow)
+        c1, c2, uf, ft = leaf(rnd(B, C, H, W)), leaf(rnd(B, C, H, W)), leaf(rnd(B, 2, H, W, scale=2.0)), leaf(rnd(B, 2, H, W))
+        run_bwd(ops.level_fused(c1, c2, uf, ft, flow_scale=1.25), c1, c2, uf, ft)
+    B, H, W = 8, 384, 512
+    i1, i2, flow = rnd(B, 3, H, W), rnd(B, 3, H, W), rnd(B, 2, H, W, scale=8.0)
+    f = leaf(flow)
+    rmap = ops.range_map(rnd(B, 2, H, W, scale=8.0).cuda())
+    photo = ops.occ_photo_fused(i1.cuda(), i2.cuda(), f, rmap, flow_gt=rnd(B, 2, H, W).cuda(),
+                                occ_gt=(torch.rand(B, 1, H, W, generator=G) < 0.3).float().cuda())[0]
+    run_bwd(photo, f)
+    a, fl = leaf(i1 * 0.01), leaf(flow)
+    run_bwd(ocf.first_order_smoothness_loss(a, fl), a, fl)
+    a, b = leaf(torch.rand(2, 3, 436, 1024, generator=G)), leaf(torch.rand(2, 3, 436, 1024, generator=G))
+    run_bwd(ocf.ssim(a, b, 11), a, b)
+    a, b = leaf(torch.rand(2, 3, 436, 1024, generator=G)), leaf(torch.rand(2, 3, 436, 1024, generator=G))
+    run_bwd(ocf.census_loss(a, b, torch.rand(2, 1, 436, 1024, generator=G).cuda(), 3), a, b)
+
+
 GROUPS = {"corr": group_corr, "normalize": group_normalize, "warp": group_warp, "scatter": group_scatter, "loss": group_loss,
-          "ssim": group_ssim, "census": group_census, "resize": group_resize, "level": group_level, "data": group_data}
+          "ssim": group_ssim, "census": group_census, "resize": group_resize, "level": group_level, "data": group_data, "big": group_big}
 
 
 def main():

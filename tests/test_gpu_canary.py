@@ -48,7 +48,7 @@ class _GuardedTorch:
         return self._carve(tuple(t.shape), t.dtype, t.device, zero=True)
 
 
-@pytest.mark.parametrize("group", ["corr", "normalize", "warp", "scatter", "loss", "ssim", "census", "resize", "level", "data"])
+@pytest.mark.parametrize("group", ["corr", "normalize", "warp", "scatter", "loss", "ssim", "census", "resize", "level", "data", "big"])
 def test_kernels_stay_inside_the_buffers_they_are_handed(group, monkeypatch):
     import sanitize_ops as S
     from ocflow_b200 import data, metrics, ops
