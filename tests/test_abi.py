@@ -61,6 +61,21 @@ def test_argument_validation_happens_before_any_launch():
     assert lib.ocf_host_corr_fwd(None, None, None, 1, 1, 1, 1, 4) == -1
 
 
+def test_every_entry_point_rejects_null_pointers_and_empty_shapes_without_a_device():
+    """The whole ABI, not a sample: all-NULL arguments give OCF_ENULL, dummy (never dereferenced) pointers with zero sizes give
+    OCF_ESHAPE / OCF_EUNSUPPORTED -- each before anything is enqueued, so this runs where there is no GPU."""
+    from ocflow_b200 import _lib
+
+    lib = _lib.load()
+    dummy = ctypes.c_void_p(4096)
+    for name, argtypes in _lib.SIGNATURES.items():
+        def args(ptr):
+            return [ptr if t is ctypes.c_void_p else (0.0 if t in (ctypes.c_float, ctypes.c_double) else 0) for t in argtypes]
+        fn = getattr(lib, name)
+        assert fn(*args(None)) == -1, name
+        assert fn(*args(dummy)) in (-2, -3), name
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     from ocflow_b200 import _lib
 
